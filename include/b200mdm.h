@@ -1,0 +1,153 @@
+/* b200mdm.h -- C ABI of libb200mdm.so: the B200 (sm_100a) sampling engine that replaces the per-step hot path of
+ * GuyTevet/motion-diffusion-model (paths below are relative to the reference repository root).
+ *
+ * The reference is pure Python, so there is no existing FFI to mirror; each entry point states which
+ * reference function(s) it replaces.  The Python host mirror (motion-diffusion-model_b200/) binds these with
+ * ctypes and passes torch tensors as raw pointers (`tensor.data_ptr()`), the CUDA stream
+ * as `torch.cuda.current_stream().cuda_stream`.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative B200MDM_E* code on failure; b200mdm_last_error() returns a
+ *     thread-local description of the most recent failure;
+ *   - pointers named *_dev are device pointers, *_host host pointers; no ownership is transferred;
+ *   - tensors use the reference's layouts: motion x [B, njoints, nfeats, T] fp32 (T contiguous),
+ *     text embedding [B, cond_dim] fp32 (the reference's [1, B, C] with the leading 1 dropped);
+ *   - nothing allocates on the per-step path: workspaces are (re)built by b200mdm_set_cond for a (B, T) pair;
+ *   - no call synchronises the stream except where stated.
+ */
+#ifndef B200MDM_H_
+#define B200MDM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MDM_OK 0
+#define B200MDM_EINVAL (-1)   /* contract violation (the reference raises AssertionError / ValueError) */
+#define B200MDM_ECUDA (-2)    /* CUDA runtime / driver error */
+#define B200MDM_ESTATE (-3)   /* call order violated (weights not finalised, schedule / cond missing ...) */
+#define B200MDM_ENOTIMPL (-4) /* configuration the engine does not implement (reference: NotImplementedError) */
+
+#define B200MDM_ARCH_TRANS_ENC 0
+#define B200MDM_ARCH_TRANS_DEC 1
+
+#define B200MDM_COND_NONE 0
+#define B200MDM_COND_TEXT 1
+#define B200MDM_COND_ACTION 2
+
+#define B200MDM_MODE_X0 0   /* model output only */
+#define B200MDM_MODE_DDPM 1 /* p_sample */
+#define B200MDM_MODE_DDIM 2 /* ddim_sample */
+
+#define B200MDM_FLAG_CONST_NOISE 1   /* p_sample(const_noise=True): eps row 0 repeated (gaussian_diffusion.py:527-528) */
+#define B200MDM_FLAG_CLIP_DENOISED 2 /* clip_denoised=True: clamp x0 to [-1,1] (gaussian_diffusion.py:348-352) */
+
+#define B200MDM_SCHED_STRIDE 8 /* floats per schedule row, see b200mdm_set_schedule */
+
+typedef struct b200mdm_engine b200mdm_engine;
+
+/* Mirrors the keyword arguments utils/model_util.py:24-71 (get_model_args) passes to MDM.__init__
+ * (model/mdm.py:12-135) that matter to the forward pass. */
+typedef struct b200mdm_config {
+  int32_t arch;              /* B200MDM_ARCH_*            (args.arch) */
+  int32_t latent_dim;        /* 512                       (args.latent_dim) */
+  int32_t ff_size;           /* 1024                      (hard-wired model_util.py:63) */
+  int32_t num_layers;        /* 8                         (args.layers) */
+  int32_t num_heads;         /* 4                         (hard-wired model_util.py:63) */
+  int32_t njoints;           /* 263 humanml / 25 a2m */
+  int32_t nfeats;            /* 1 humanml / 6 a2m */
+  int32_t cond_mode;         /* B200MDM_COND_*            (utils/parser_util.py:269-276) */
+  int32_t cond_dim;          /* 512 CLIP / 768 DistilBERT (model/mdm.py:121) */
+  int32_t num_actions;       /* rows of embed_action.action_embedding */
+  int32_t mask_frames;       /* args.mask_frames (model/mdm.py:241-247) */
+  int32_t pos_embed_max_len; /* args.pos_embed_max_len: rows of the positional table */
+  int32_t temb_rows;         /* model timesteps to pre-embed (>= original_num_steps of the diffusion) */
+  int32_t reserved[7];
+} b200mdm_config;
+
+const char* b200mdm_last_error(void);
+int b200mdm_version(void);
+
+/* MDM.__init__ (model/mdm.py:12-135): allocates the weight store for `cfg` on the current CUDA device. */
+int b200mdm_create(const b200mdm_config* cfg, b200mdm_engine** out);
+int b200mdm_destroy(b200mdm_engine* e);
+
+/* load_model_wo_clip / load_state_dict(strict=False) (utils/model_util.py:8-15): one call per state_dict entry,
+ * `name` is the reference key, data fp32, host or device memory.  "sequence_pos_encoder.pe"
+ * ([max_len, d]; the buffer the reference recomputes in PositionalEncoding.__init__, model/mdm.py:301-308) is
+ * accepted here as well.  Unknown names -> B200MDM_EINVAL (the reference asserts no unexpected keys). */
+int b200mdm_load_weight(b200mdm_engine* e, const char* name, const float* data, const int64_t* shape, int32_t ndim);
+
+/* Repack for the tensor cores (fp16 K-major copies, hi/lo split of the in/out projections), precompute the
+ * timestep-embedding MLP (TimestepEmbedder.forward, model/mdm.py:329-330) for every model timestep.
+ * Fails with B200MDM_ESTATE listing the first missing tensor. */
+int b200mdm_finalize_weights(b200mdm_engine* e, void* stream);
+
+/* SpacedDiffusion / GaussianDiffusion tables (diffusion/respace.py:74-88, gaussian_diffusion.py:166-205) after the
+ * fp64->fp32 cast of _extract_into_tensor (gaussian_diffusion.py:1612).  rows_host: n_steps rows of
+ *   [0] posterior_mean_coef1  [1] posterior_mean_coef2  [2] (t!=0) * exp(0.5*posterior_log_variance_clipped)
+ *   [3] sqrt_recip_alphas_cumprod  [4] sqrt_recipm1_alphas_cumprod  [5] sqrt(alphas_cumprod_prev)
+ *   [6] sqrt(1 - alphas_cumprod_prev - sigma_ddim^2)  [7] (t!=0) * sigma_ddim(eta)
+ * timestep_map_host: _WrappedModel's map (respace.py:125-127), n_steps int32.  Synchronous copy. */
+int b200mdm_set_schedule(b200mdm_engine* e, int32_t n_steps, const float* rows_host, const int32_t* timestep_map_host);
+
+/* Canonicalises model_kwargs['y'] (data_loaders/tensors.py:22-64 + callers) once per loop and (re)builds the
+ * workspace for (batch, nframes):
+ *   cond_embed_dev : y['text_embed'][0]  [batch, cond_dim] fp32 device, or NULL (cond_mode none / action)
+ *   lengths_host   : y['lengths'] int64 [batch] or NULL => no key mask (also ignored unless cfg.mask_frames)
+ *   scale_dev      : y['scale'] fp32 [batch] device => ClassifierFreeSampleModel semantics (cond/uncond pair
+ *                    packed into one batch of 2*batch, utils/sampler_util.py:27-34); NULL => single forward
+ *   force_uncond   : y.get('uncond', False) for the single-forward case (model/mdm.py:208)
+ *   action_host    : y['action'][:,0] int64 [batch] or NULL
+ * The text projection embed_text(mask_cond(.)) (model/mdm.py:218) is evaluated here, once. */
+int b200mdm_set_cond(b200mdm_engine* e, int32_t batch, int32_t nframes, const float* cond_embed_dev,
+                     const int64_t* lengths_host, const float* scale_dev, int32_t force_uncond,
+                     const int64_t* action_host, void* stream);
+
+/* y['inpainting_mask'] (bool as uint8) / y['inpainted_motion'] [B,J,F,T] device pointers
+ * (gaussian_diffusion.py:300-304); NULL, NULL clears. */
+int b200mdm_set_inpaint(b200mdm_engine* e, const uint8_t* mask_dev, const float* motion_dev);
+
+/* MDM.forward / ClassifierFreeSampleModel.forward (model/mdm.py:189-283, utils/sampler_util.py:27-34):
+ * out = model(x, timesteps, y).  timesteps_host: int32 [batch] MODEL timesteps (already mapped). */
+int b200mdm_denoise(b200mdm_engine* e, const float* x_dev, const int32_t* timesteps_host, float* out_dev, void* stream);
+
+/* One p_sample / ddim_sample (gaussian_diffusion.py:489-541 / 729-779) at schedule index `index`:
+ * x_out = step(x_t, eps).  pred_xstart_dev may be NULL.  x_out_dev may alias x_t_dev. */
+int b200mdm_sample_step(b200mdm_engine* e, int32_t mode, int32_t index, const float* x_t_dev, const float* noise_dev,
+                        int32_t flags, float* x_out_dev, float* pred_xstart_dev, void* stream);
+
+/* p_sample_loop / ddim_sample_loop (gaussian_diffusion.py:591-727 / 876-990) without returning to the host:
+ * steps index = n_steps-1-skip_timesteps ... 0 are enqueued on `stream` (one CUDA graph of a single step,
+ * replayed, when use_graph != 0).  x_dev holds x_T on entry (after any q_sample of init_image) and x_0 on
+ * exit (in place).  noise_tape_dev: eps for step k at noise_tape_dev + k*noise_step_stride elements
+ * (k = 0 is the first executed step).  pred_xstart_dev may be NULL. */
+int b200mdm_sample_loop(b200mdm_engine* e, int32_t mode, int32_t skip_timesteps, float* x_dev,
+                        const float* noise_tape_dev, int64_t noise_step_stride, int32_t flags,
+                        float* pred_xstart_dev, int32_t use_graph, void* stream);
+
+/* q_sample (gaussian_diffusion.py:226-244) at schedule index `index`: out = sqrt_ac*x_start + sqrt_1mac*noise;
+ * x_start_dev NULL => zeros (gaussian_diffusion.py:693-694).  sqrt_ac / sqrt_1mac are the fp32 table values. */
+int b200mdm_q_sample(b200mdm_engine* e, float sqrt_ac, float sqrt_1mac, const float* x_start_dev,
+                     const float* noise_dev, float* out_dev, int64_t n, void* stream);
+
+/* Kernels launched by this engine since creation / since the last reset (bench.py's gpu_launches). */
+int64_t b200mdm_launch_count(b200mdm_engine* e, int32_t reset);
+
+/* ---- kernel-level entry points (used by tests/ to check each kernel against a torch fp32 restatement) ---- */
+/* out16[M,N] = fp16(act(A16[M,K] @ W16[N,K]^T + bias)); act: 0 none, 1 exact GELU.  K % 8 == 0, N % 2 == 0. */
+int b200mdm_test_gemm_f16(const void* a16_dev, const void* w16_dev, const float* bias_dev, void* out16_dev, int32_t M,
+                          int32_t N, int32_t K, int32_t act, int32_t block_n, void* stream);
+/* out16[n*S, d] = softmax(q k^T / sqrt(128) + mask) v per (sample, head); qkv16 [n*S, 3d]; kvlen int32 [n] device */
+int b200mdm_test_attention(const void* qkv16_dev, void* out16_dev, const int32_t* kvlen_dev, int32_t n_samples,
+                           int32_t S, int32_t d, void* stream);
+/* in-place LayerNorm over rows of h32 [M,512] + fp16 copy */
+int b200mdm_test_layernorm(float* h32_dev, void* h16_dev, const float* gamma_dev, const float* beta_dev, int32_t M,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MDM_H_ */

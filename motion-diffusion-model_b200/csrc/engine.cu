@@ -1,0 +1,795 @@
+// libb200mdm.so -- C-ABI engine (see include/b200mdm.h for the contract and the reference lines each entry
+// point replaces).  Host side: weight store + repack, TMA descriptor set-up, per-(B,T) workspace, launch
+// sequences for one denoiser forward / one sampler step, and the whole-loop driver (one CUDA graph of a single
+// step, replayed; per-step scalars are read from device tables indexed by a device-side step counter so the
+// graph never changes).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b200mdm.h"
+#include "attention.cuh"
+#include "epilogues.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+using namespace b200;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                               \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return fail(B200MDM_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define TRY(expr)            \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != B200MDM_OK) return _r; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ TMA maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int resolve_driver() {
+  if (g_encode) return B200MDM_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(B200MDM_ECUDA, "cuTensorMapEncodeTiled not available");
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return B200MDM_OK;
+}
+// fp16 matrix [rows, cols] with leading dimension ld (elements); box = box_rows x 64 columns, 128-byte swizzle.
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  TRY(resolve_driver());
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16) return fail(B200MDM_EINVAL, "TMA operand misaligned");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * 2};
+  cuuint32_t box[2] = {GEMM_BLOCK_K, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200MDM_ECUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  return B200MDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ engine
+struct Tensor32 {
+  float* dev = nullptr;
+  std::vector<int64_t> shape;
+  size_t numel = 0;
+};
+
+struct LayerW {
+  __half *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+  const float *bqkv, *bo, *b1, *b2, *g1, *be1, *g2, *be2;
+  CUtensorMap m_wqkv, m_wo, m_w1, m_w2;
+};
+
+struct GraphKey {
+  int mode = -1, B = 0, T = 0, const_noise = 0;
+  const void *x = nullptr, *noise = nullptr, *pred = nullptr, *imask = nullptr, *imotion = nullptr;
+  long long stride = 0;
+  bool operator==(const GraphKey& o) const {
+    return mode == o.mode && B == o.B && T == o.T && const_noise == o.const_noise && x == o.x && noise == o.noise &&
+           pred == o.pred && imask == o.imask && imotion == o.imotion && stride == o.stride;
+  }
+};
+
+struct b200mdm_engine {
+  b200mdm_config cfg;
+  int d, ff, L, H, JF, Kp_in, N_out_pad;
+  int num_sms = 148;
+  std::map<std::string, Tensor32> store;
+  bool finalized = false;
+  // repacked weights
+  __half *w_in3 = nullptr, *w_out3 = nullptr;
+  CUtensorMap m_win, m_wout;
+  std::vector<LayerW> layers;
+  const float *b_in = nullptr, *b_out = nullptr, *pe = nullptr, *w_txt = nullptr, *b_txt = nullptr, *act_emb = nullptr;
+  float *temb_hidden = nullptr, *temb_table = nullptr;
+  // schedule
+  float* sched = nullptr;
+  int* tmap = nullptr;
+  int n_steps = 0;
+  // per-(B,T) workspace
+  int B = 0, T = 0, S = 0, halves = 1, Bp = 0, M = 0, MB = 0;
+  __half *xin16 = nullptr, *h16 = nullptr, *qkv16 = nullptr, *att16 = nullptr, *ffn16 = nullptr, *g16 = nullptr;
+  float *h32 = nullptr, *tok0 = nullptr, *condproj = nullptr, *proj = nullptr, *scale = nullptr;
+  int *kvlen = nullptr, *tvec = nullptr, *action = nullptr;
+  StepState* state = nullptr;
+  CUtensorMap m_xin, m_h16, m_att, m_ffn, m_g16;
+  bool cond_set = false;
+  const unsigned char* inpaint_mask = nullptr;
+  const float* inpaint_motion = nullptr;
+  // loop machinery
+  cudaStream_t work = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  GraphKey graph_key;
+  int graph_kernels = 0;
+  long long launches = 0;
+};
+
+template <class T>
+static int dalloc(T** p, size_t n, bool zero = false) {
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  if (zero) CUDA_TRY(cudaMemset(*p, 0, n * sizeof(T)));
+  return B200MDM_OK;
+}
+template <class T>
+static void dfree(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+template <int BN, class Epi>
+static int set_gemm_attr() {
+  CUDA_TRY(cudaFuncSetAttribute(gemm_f16_tcgen05<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GemmSmem<BN>::TOTAL));
+  return B200MDM_OK;
+}
+static int init_kernel_attrs() {
+  static bool done = false;
+  if (done) return B200MDM_OK;
+  TRY((set_gemm_attr<256, EpiBiasF16<false>>()));
+  TRY((set_gemm_attr<256, EpiBiasF16<true>>()));
+  TRY((set_gemm_attr<128, EpiBiasF16<false>>()));
+  TRY((set_gemm_attr<128, EpiBiasF16<true>>()));
+  TRY((set_gemm_attr<96, EpiBiasF16<false>>()));
+  TRY((set_gemm_attr<96, EpiBiasF16<true>>()));
+  TRY((set_gemm_attr<256, EpiResidualF32>()));
+  TRY((set_gemm_attr<128, EpiEmbed>()));
+  TRY((set_gemm_attr<96, EpiOutStep>()));
+  CUDA_TRY(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  done = true;
+  return B200MDM_OK;
+}
+
+template <int BN, class Epi>
+static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, int M, int N, int K, const typename Epi::Params& p,
+                       cudaStream_t s, int num_sms) {
+  const int tiles = ((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((N + BN - 1) / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_f16_tcgen05<BN, Epi><<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, s>>>(a, b, M, N, K, p);
+  CUDA_TRY(cudaGetLastError());
+  return B200MDM_OK;
+}
+
+static int launch_attention(const __half* qkv, __half* out, const int* kvlen, int n_samples, int S, int d, int H,
+                            cudaStream_t s) {
+  const int S_pad = (S + 15) & ~15;
+  const size_t smem = static_cast<size_t>(S_pad) * 512;
+  if (smem > 220 * 1024) return fail(B200MDM_ENOTIMPL, "attention: sequence of %d tokens exceeds the resident-KV kernel", S);
+  if (d != H * ATT_DH) return fail(B200MDM_ENOTIMPL, "attention: head_dim must be 128");
+  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(ATT_DH));
+  attention_mma_kernel<<<dim3(H, n_samples), ATT_THREADS, smem, s>>>(qkv, out, kvlen, S, d, scale_log2);
+  CUDA_TRY(cudaGetLastError());
+  return B200MDM_OK;
+}
+
+static int launch_layernorm(float* h32, __half* h16, const float* g, const float* b, int M, cudaStream_t s) {
+  layernorm512_kernel<<<(M + 7) / 8, 256, 0, s>>>(h32, h16, g, b, M, 1e-5f);
+  CUDA_TRY(cudaGetLastError());
+  return B200MDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ API: basics
+extern "C" const char* b200mdm_last_error(void) { return g_err; }
+extern "C" int b200mdm_version(void) { return 1; }
+
+extern "C" int b200mdm_create(const b200mdm_config* cfg, b200mdm_engine** out) {
+  if (!cfg || !out) return fail(B200MDM_EINVAL, "null argument");
+  if (cfg->arch != B200MDM_ARCH_TRANS_ENC)
+    return fail(B200MDM_ENOTIMPL, "arch %d: only trans_enc is implemented in this revision", cfg->arch);
+  if (cfg->latent_dim != 512 || cfg->num_heads != 4 || cfg->ff_size % 64 || cfg->ff_size <= 0)
+    return fail(B200MDM_ENOTIMPL, "kernels are specialised for latent_dim 512 / 4 heads (got %d / %d)", cfg->latent_dim,
+                cfg->num_heads);
+  if (cfg->num_layers <= 0 || cfg->njoints <= 0 || cfg->nfeats <= 0 || cfg->pos_embed_max_len <= 0 || cfg->temb_rows <= 0)
+    return fail(B200MDM_EINVAL, "bad config");
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(B200MDM_ECUDA, "sm_100a device required (found sm_%d%d)", prop.major, prop.minor);
+  TRY(init_kernel_attrs());
+  TRY(resolve_driver());
+  b200mdm_engine* e = new b200mdm_engine();
+  e->cfg = *cfg;
+  e->d = cfg->latent_dim;
+  e->ff = cfg->ff_size;
+  e->L = cfg->num_layers;
+  e->H = cfg->num_heads;
+  e->JF = cfg->njoints * cfg->nfeats;
+  e->Kp_in = (e->JF + 7) & ~7;
+  e->N_out_pad = ((e->JF + 95) / 96) * 96;
+  e->num_sms = prop.multiProcessorCount;
+  e->layers.resize(e->L);
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->work, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+  TRY(dalloc(&e->state, 1, true));
+  *out = e;
+  return B200MDM_OK;
+}
+
+static void free_workspace(b200mdm_engine* e) {
+  dfree(e->xin16); dfree(e->h16); dfree(e->qkv16); dfree(e->att16); dfree(e->ffn16); dfree(e->g16);
+  dfree(e->h32); dfree(e->tok0); dfree(e->condproj); dfree(e->proj); dfree(e->scale);
+  dfree(e->kvlen); dfree(e->tvec); dfree(e->action);
+  e->B = e->T = 0;
+  e->cond_set = false;
+}
+static void drop_graph(b200mdm_engine* e) {
+  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  e->graph_exec = nullptr;
+  e->graph_key = GraphKey();
+}
+
+extern "C" int b200mdm_destroy(b200mdm_engine* e) {
+  if (!e) return B200MDM_OK;
+  cudaDeviceSynchronize();
+  drop_graph(e);
+  free_workspace(e);
+  for (auto& kv : e->store) cudaFree(kv.second.dev);
+  for (auto& l : e->layers) { dfree(l.wqkv); dfree(l.wo); dfree(l.w1); dfree(l.w2); }
+  dfree(e->w_in3); dfree(e->w_out3); dfree(e->temb_hidden); dfree(e->temb_table); dfree(e->sched); dfree(e->tmap);
+  dfree(e->state);
+  if (e->work) cudaStreamDestroy(e->work);
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_out) cudaEventDestroy(e->ev_out);
+  delete e;
+  return B200MDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+static bool known_weight_name(const b200mdm_engine* e, const std::string& n) {
+  static const char* fixed[] = {"input_process.poseEmbedding.weight", "input_process.poseEmbedding.bias",
+                                "embed_timestep.time_embed.0.weight", "embed_timestep.time_embed.0.bias",
+                                "embed_timestep.time_embed.2.weight", "embed_timestep.time_embed.2.bias",
+                                "embed_text.weight", "embed_text.bias", "embed_action.action_embedding",
+                                "output_process.poseFinal.weight", "output_process.poseFinal.bias",
+                                "sequence_pos_encoder.pe", "embed_timestep.sequence_pos_encoder.pe"};
+  for (const char* f : fixed)
+    if (n == f) return true;
+  static const char* per_layer[] = {"self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight",
+                                    "self_attn.out_proj.bias", "linear1.weight", "linear1.bias", "linear2.weight",
+                                    "linear2.bias", "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias"};
+  const std::string pre = "seqTransEncoder.layers.";
+  if (n.compare(0, pre.size(), pre) == 0) {
+    size_t dot = n.find('.', pre.size());
+    if (dot == std::string::npos) return false;
+    int l = atoi(n.substr(pre.size(), dot - pre.size()).c_str());
+    if (l < 0 || l >= e->L) return false;
+    std::string rest = n.substr(dot + 1);
+    for (const char* f : per_layer)
+      if (rest == f) return true;
+  }
+  return false;
+}
+
+extern "C" int b200mdm_load_weight(b200mdm_engine* e, const char* name, const float* data, const int64_t* shape,
+                                   int32_t ndim) {
+  if (!e || !name || !data || !shape || ndim < 1 || ndim > 4) return fail(B200MDM_EINVAL, "bad argument");
+  std::string n(name);
+  if (!known_weight_name(e, n)) return fail(B200MDM_EINVAL, "unexpected state_dict key '%s'", name);
+  size_t numel = 1;
+  std::vector<int64_t> shp(shape, shape + ndim);
+  for (int64_t s : shp) {
+    if (s <= 0) return fail(B200MDM_EINVAL, "bad shape for '%s'", name);
+    numel *= static_cast<size_t>(s);
+  }
+  Tensor32& t = e->store[n];
+  if (t.dev && t.numel != numel) { cudaFree(t.dev); t.dev = nullptr; }
+  if (!t.dev) TRY(dalloc(&t.dev, numel));
+  t.shape = shp;
+  t.numel = numel;
+  CUDA_TRY(cudaMemcpy(t.dev, data, numel * sizeof(float), cudaMemcpyDefault));
+  e->finalized = false;
+  return B200MDM_OK;
+}
+
+static int need(b200mdm_engine* e, const std::string& name, std::initializer_list<int64_t> shape, const float** out) {
+  auto it = e->store.find(name);
+  if (it == e->store.end()) return fail(B200MDM_ESTATE, "missing weight '%s'", name.c_str());
+  std::vector<int64_t> want(shape);
+  // allow a leading singleton / trailing squeeze for the positional table [max_len, 1, d]
+  size_t numel = 1;
+  for (int64_t s : want) numel *= static_cast<size_t>(s);
+  if (it->second.numel != numel) return fail(B200MDM_EINVAL, "weight '%s' has %zu elements, expected %zu", name.c_str(), it->second.numel, numel);
+  *out = it->second.dev;
+  return B200MDM_OK;
+}
+
+static int to_f16(const float* src, __half** dst, size_t n, cudaStream_t s) {
+  TRY(dalloc(dst, n));
+  f32_to_f16_kernel<<<512, 256, 0, s>>>(src, *dst, n);
+  CUDA_TRY(cudaGetLastError());
+  return B200MDM_OK;
+}
+
+extern "C" int b200mdm_finalize_weights(b200mdm_engine* e, void* stream) {
+  if (!e) return fail(B200MDM_EINVAL, "null engine");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int d = e->d, ff = e->ff, JF = e->JF;
+  const float *w_in, *w_out, *t0w, *t0b, *t2w, *t2b;
+  TRY(need(e, "input_process.poseEmbedding.weight", {d, JF}, &w_in));
+  TRY(need(e, "input_process.poseEmbedding.bias", {d}, &e->b_in));
+  TRY(need(e, "output_process.poseFinal.weight", {JF, d}, &w_out));
+  TRY(need(e, "output_process.poseFinal.bias", {JF}, &e->b_out));
+  TRY(need(e, "embed_timestep.time_embed.0.weight", {d, d}, &t0w));
+  TRY(need(e, "embed_timestep.time_embed.0.bias", {d}, &t0b));
+  TRY(need(e, "embed_timestep.time_embed.2.weight", {d, d}, &t2w));
+  TRY(need(e, "embed_timestep.time_embed.2.bias", {d}, &t2b));
+  TRY(need(e, "sequence_pos_encoder.pe", {e->cfg.pos_embed_max_len, d}, &e->pe));
+  if (e->cfg.cond_mode == B200MDM_COND_TEXT) {
+    TRY(need(e, "embed_text.weight", {d, e->cfg.cond_dim}, &e->w_txt));
+    TRY(need(e, "embed_text.bias", {d}, &e->b_txt));
+  } else if (e->cfg.cond_mode == B200MDM_COND_ACTION) {
+    TRY(need(e, "embed_action.action_embedding", {e->cfg.num_actions, d}, &e->act_emb));
+  }
+  if (e->cfg.temb_rows > e->cfg.pos_embed_max_len) return fail(B200MDM_EINVAL, "temb_rows exceeds the positional table");
+
+  // drop previous repacks
+  drop_graph(e);
+  for (auto& l : e->layers) { dfree(l.wqkv); dfree(l.wo); dfree(l.w1); dfree(l.w2); }
+  dfree(e->w_in3); dfree(e->w_out3); dfree(e->temb_hidden); dfree(e->temb_table);
+
+  // split-precision in / out projections: W' = [hi | hi | lo], zero padded
+  const int Kp = e->Kp_in;
+  TRY(dalloc(&e->w_in3, static_cast<size_t>(d) * 3 * Kp, true));
+  split_weight_kernel<<<d, 128, 0, s>>>(w_in, e->w_in3, d, JF, Kp);
+  CUDA_TRY(cudaGetLastError());
+  TRY(dalloc(&e->w_out3, static_cast<size_t>(e->N_out_pad) * 3 * d, true));
+  split_weight_kernel<<<JF, 128, 0, s>>>(w_out, e->w_out3, JF, d, d);
+  CUDA_TRY(cudaGetLastError());
+  TRY(make_map(&e->m_win, e->w_in3, d, 3 * Kp, 3 * Kp, 128));
+  TRY(make_map(&e->m_wout, e->w_out3, e->N_out_pad, 3 * d, 3 * d, 96));
+
+  for (int l = 0; l < e->L; ++l) {
+    LayerW& w = e->layers[l];
+    const std::string p = "seqTransEncoder.layers." + std::to_string(l) + ".";
+    const float *wqkv, *wo, *w1, *w2;
+    TRY(need(e, p + "self_attn.in_proj_weight", {3 * d, d}, &wqkv));
+    TRY(need(e, p + "self_attn.in_proj_bias", {3 * d}, &w.bqkv));
+    TRY(need(e, p + "self_attn.out_proj.weight", {d, d}, &wo));
+    TRY(need(e, p + "self_attn.out_proj.bias", {d}, &w.bo));
+    TRY(need(e, p + "linear1.weight", {ff, d}, &w1));
+    TRY(need(e, p + "linear1.bias", {ff}, &w.b1));
+    TRY(need(e, p + "linear2.weight", {d, ff}, &w2));
+    TRY(need(e, p + "linear2.bias", {d}, &w.b2));
+    TRY(need(e, p + "norm1.weight", {d}, &w.g1));
+    TRY(need(e, p + "norm1.bias", {d}, &w.be1));
+    TRY(need(e, p + "norm2.weight", {d}, &w.g2));
+    TRY(need(e, p + "norm2.bias", {d}, &w.be2));
+    TRY(to_f16(wqkv, &w.wqkv, static_cast<size_t>(3) * d * d, s));
+    TRY(to_f16(wo, &w.wo, static_cast<size_t>(d) * d, s));
+    TRY(to_f16(w1, &w.w1, static_cast<size_t>(ff) * d, s));
+    TRY(to_f16(w2, &w.w2, static_cast<size_t>(d) * ff, s));
+    TRY(make_map(&w.m_wqkv, w.wqkv, 3 * d, d, d, 256));
+    TRY(make_map(&w.m_wo, w.wo, d, d, d, 256));
+    TRY(make_map(&w.m_w1, w.w1, ff, d, d, 256));
+    TRY(make_map(&w.m_w2, w.w2, d, ff, ff, 256));
+  }
+  // timestep-embedding MLP for every model timestep: temb[t] = W2 silu(W1 pe[t] + b1) + b2
+  const int R = e->cfg.temb_rows;
+  TRY(dalloc(&e->temb_hidden, static_cast<size_t>(R) * d));
+  TRY(dalloc(&e->temb_table, static_cast<size_t>(R) * d));
+  const size_t warps = static_cast<size_t>(R) * d;
+  const int blocks = static_cast<int>((warps * 32 + 255) / 256);
+  small_linear_kernel<1><<<blocks, 256, 0, s>>>(e->pe, t0w, t0b, e->temb_hidden, R, d, d, d);
+  CUDA_TRY(cudaGetLastError());
+  small_linear_kernel<0><<<blocks, 256, 0, s>>>(e->temb_hidden, t2w, t2b, e->temb_table, R, d, d, d);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(s));
+  e->finalized = true;
+  return B200MDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ schedule
+extern "C" int b200mdm_set_schedule(b200mdm_engine* e, int32_t n_steps, const float* rows_host,
+                                    const int32_t* timestep_map_host) {
+  if (!e || n_steps <= 0 || !rows_host || !timestep_map_host) return fail(B200MDM_EINVAL, "bad argument");
+  for (int i = 0; i < n_steps; ++i)
+    if (timestep_map_host[i] < 0 || timestep_map_host[i] >= e->cfg.temb_rows)
+      return fail(B200MDM_EINVAL, "timestep_map[%d] = %d outside the pre-embedded range [0, %d)", i, timestep_map_host[i],
+                  e->cfg.temb_rows);
+  if (n_steps != e->n_steps) {
+    dfree(e->sched);
+    dfree(e->tmap);
+    TRY(dalloc(&e->sched, static_cast<size_t>(n_steps) * SCHED_STRIDE));
+    TRY(dalloc(&e->tmap, n_steps));
+    e->n_steps = n_steps;
+  }
+  CUDA_TRY(cudaDeviceSynchronize());  // a loop still in flight may be reading the old tables
+  CUDA_TRY(cudaMemcpy(e->sched, rows_host, static_cast<size_t>(n_steps) * SCHED_STRIDE * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(e->tmap, timestep_map_host, static_cast<size_t>(n_steps) * sizeof(int), cudaMemcpyHostToDevice));
+  return B200MDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ cond / workspace
+static int build_workspace(b200mdm_engine* e, int B, int T, int halves) {
+  drop_graph(e);
+  free_workspace(e);
+  const int d = e->d, S = T + 1, Bp = halves * B;
+  const size_t M = static_cast<size_t>(Bp) * S, MB = static_cast<size_t>(B) * S;
+  TRY(dalloc(&e->xin16, MB * 3 * e->Kp_in, true));
+  TRY(dalloc(&e->h16, M * d));
+  TRY(dalloc(&e->h32, M * d));
+  TRY(dalloc(&e->qkv16, M * 3 * d));
+  TRY(dalloc(&e->att16, M * d));
+  TRY(dalloc(&e->ffn16, M * e->ff));
+  TRY(dalloc(&e->g16, MB * 3 * d));
+  TRY(dalloc(&e->tok0, static_cast<size_t>(Bp) * d));
+  TRY(dalloc(&e->condproj, static_cast<size_t>(Bp) * d, true));
+  TRY(dalloc(&e->proj, static_cast<size_t>(B) * d, true));
+  TRY(dalloc(&e->scale, B, true));
+  TRY(dalloc(&e->kvlen, Bp));
+  TRY(dalloc(&e->tvec, B, true));
+  TRY(dalloc(&e->action, B, true));
+  e->B = B; e->T = T; e->S = S; e->halves = halves; e->Bp = Bp;
+  e->M = static_cast<int>(M); e->MB = static_cast<int>(MB);
+  TRY(make_map(&e->m_xin, e->xin16, MB, 3 * e->Kp_in, 3 * e->Kp_in, GEMM_BLOCK_M));
+  TRY(make_map(&e->m_h16, e->h16, M, d, d, GEMM_BLOCK_M));
+  TRY(make_map(&e->m_att, e->att16, M, d, d, GEMM_BLOCK_M));
+  TRY(make_map(&e->m_ffn, e->ffn16, M, e->ff, e->ff, GEMM_BLOCK_M));
+  TRY(make_map(&e->m_g16, e->g16, MB, 3 * d, 3 * d, GEMM_BLOCK_M));
+  return B200MDM_OK;
+}
+
+extern "C" int b200mdm_set_cond(b200mdm_engine* e, int32_t batch, int32_t nframes, const float* cond_embed_dev,
+                                const int64_t* lengths_host, const float* scale_dev, int32_t force_uncond,
+                                const int64_t* action_host, void* stream) {
+  if (!e) return fail(B200MDM_EINVAL, "null engine");
+  if (!e->finalized) return fail(B200MDM_ESTATE, "weights not finalised");
+  if (batch <= 0 || nframes <= 0) return fail(B200MDM_EINVAL, "bad batch / nframes");
+  if (nframes + 1 > e->cfg.pos_embed_max_len) return fail(B200MDM_EINVAL, "sequence longer than the positional table");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int halves = scale_dev ? 2 : 1;
+  if (e->cfg.cond_mode == B200MDM_COND_TEXT && !cond_embed_dev && !(halves == 1 && force_uncond))
+    return fail(B200MDM_EINVAL, "text-conditioned model needs y['text_embed']");
+  if (e->cfg.cond_mode == B200MDM_COND_ACTION && !action_host && !(halves == 1 && force_uncond))
+    return fail(B200MDM_EINVAL, "action-conditioned model needs y['action']");
+  if (halves == 2 && e->cfg.cond_mode == B200MDM_COND_NONE)
+    return fail(B200MDM_EINVAL, "classifier-free guidance needs a conditioned model (sampler_util.py:29)");
+  if (batch != e->B || nframes != e->T || halves != e->halves) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    TRY(build_workspace(e, batch, nframes, halves));
+  }
+  const int d = e->d, B = batch, S = nframes + 1;
+  // key mask -> valid-key counts (model/mdm.py:241-247; lengths_to_mask, data_loaders/tensors.py:3-6)
+  std::vector<int> kv(e->Bp, S);
+  if (e->cfg.mask_frames && lengths_host && nframes > 1) {
+    for (int b = 0; b < e->Bp; ++b) {
+      long long len = lengths_host[b % B];
+      if (len < 0) len = 0;
+      if (len > nframes) len = nframes;
+      kv[b] = static_cast<int>(len) + 1;
+    }
+  }
+  CUDA_TRY(cudaMemcpyAsync(e->kvlen, kv.data(), kv.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  if (scale_dev) CUDA_TRY(cudaMemcpyAsync(e->scale, scale_dev, B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (e->cfg.cond_mode == B200MDM_COND_ACTION && action_host) {
+    std::vector<int> a(B);
+    for (int b = 0; b < B; ++b) {
+      if (action_host[b] < 0 || action_host[b] >= e->cfg.num_actions) return fail(B200MDM_EINVAL, "action index out of range");
+      a[b] = static_cast<int>(action_host[b]);
+    }
+    CUDA_TRY(cudaMemcpyAsync(e->action, a.data(), B * sizeof(int), cudaMemcpyHostToDevice, s));
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));  // host staging vectors go out of scope
+  if (e->cfg.cond_mode == B200MDM_COND_TEXT && cond_embed_dev) {
+    const size_t warps = static_cast<size_t>(B) * d;
+    small_linear_kernel<0><<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, s>>>(cond_embed_dev, e->w_txt, e->b_txt, e->proj, B,
+                                                                                       d, e->cfg.cond_dim, e->cfg.cond_dim);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+  }
+  condproj_fill_kernel<<<e->Bp, 128, 0, s>>>(e->condproj, e->proj, e->b_txt, e->act_emb, e->action, B, d, e->Bp,
+                                             (halves == 1 && force_uncond) ? 1 : 0, e->cfg.cond_mode);
+  CUDA_TRY(cudaGetLastError());
+  e->launches++;
+  e->cond_set = true;
+  return B200MDM_OK;
+}
+
+extern "C" int b200mdm_set_inpaint(b200mdm_engine* e, const uint8_t* mask_dev, const float* motion_dev) {
+  if (!e) return fail(B200MDM_EINVAL, "null engine");
+  if ((mask_dev == nullptr) != (motion_dev == nullptr)) return fail(B200MDM_EINVAL, "inpainting needs both mask and motion");
+  e->inpaint_mask = mask_dev;
+  e->inpaint_motion = motion_dev;
+  return B200MDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+struct StepArgs {
+  int mode = B200MDM_MODE_X0;
+  const float* x_in = nullptr;    // [B, JF, T] input to the denoiser (x_t)
+  const float* noise = nullptr;
+  long long noise_step_stride = 0;
+  int const_noise = 0;
+  int clip = 0;
+  float* x_out = nullptr;
+  float* pred = nullptr;
+  bool explicit_t = false;        // use e->tvec instead of timestep_map[state.cur]
+};
+
+// Enqueue one denoiser forward (+ fused sampler step) on stream s.  Returns the number of kernels launched.
+static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s, int* n_kernels) {
+  const int d = e->d, ff = e->ff, B = e->B, T = e->T, S = e->S, JF = e->JF, Kp = e->Kp_in;
+  int nk = 0;
+  {
+    dim3 grid((T + 31) / 32, (JF + 31) / 32, B), block(32, 8);
+    pack_input_kernel<<<grid, block, 0, s>>>(a.x_in, e->xin16, B, JF, T, S, Kp, 3 * Kp, 1);
+    CUDA_TRY(cudaGetLastError());
+    ++nk;
+  }
+  tok0_kernel<<<e->Bp, 128, 0, s>>>(e->tok0, e->condproj, e->temb_table, a.explicit_t ? e->tvec : nullptr, e->tmap,
+                                    e->state, B, d, e->cfg.temb_rows);
+  CUDA_TRY(cudaGetLastError());
+  ++nk;
+  {
+    EpiEmbed::Params p{e->h32, e->h16, e->b_in, e->pe, e->tok0, B, S, d, e->halves};
+    TRY((launch_gemm<128, EpiEmbed>(e->m_xin, e->m_win, e->MB, d, 3 * Kp, p, s, e->num_sms)));
+    ++nk;
+  }
+  for (int l = 0; l < e->L; ++l) {
+    const LayerW& w = e->layers[l];
+    {
+      EpiBiasF16<false>::Params p{e->qkv16, w.bqkv, 3 * d};
+      TRY((launch_gemm<256, EpiBiasF16<false>>(e->m_h16, w.m_wqkv, e->M, 3 * d, d, p, s, e->num_sms)));
+    }
+    TRY(launch_attention(e->qkv16, e->att16, e->kvlen, e->Bp, S, d, e->H, s));
+    {
+      EpiResidualF32::Params p{e->h32, w.bo, d};
+      TRY((launch_gemm<256, EpiResidualF32>(e->m_att, w.m_wo, e->M, d, d, p, s, e->num_sms)));
+    }
+    TRY(launch_layernorm(e->h32, e->h16, w.g1, w.be1, e->M, s));
+    {
+      EpiBiasF16<true>::Params p{e->ffn16, w.b1, ff};
+      TRY((launch_gemm<256, EpiBiasF16<true>>(e->m_h16, w.m_w1, e->M, ff, d, p, s, e->num_sms)));
+    }
+    {
+      EpiResidualF32::Params p{e->h32, w.b2, d};
+      TRY((launch_gemm<256, EpiResidualF32>(e->m_ffn, w.m_w2, e->M, d, ff, p, s, e->num_sms)));
+    }
+    TRY(launch_layernorm(e->h32, e->h16, w.g2, w.be2, e->M, s));
+    nk += 7;
+  }
+  blend_split_kernel<<<(e->MB + 7) / 8, 256, 0, s>>>(e->h32, e->g16, e->scale, B, S, d, e->halves);
+  CUDA_TRY(cudaGetLastError());
+  ++nk;
+  {
+    EpiOutStep::Params p;
+    p.bias = e->b_out;
+    p.x_t = a.x_in;
+    p.noise = a.noise;
+    p.x_out = a.x_out;
+    p.pred_xstart = a.pred;
+    p.inpaint_mask = e->inpaint_mask;
+    p.inpaint_motion = e->inpaint_motion;
+    p.sched = e->sched;
+    p.state = e->state;
+    p.noise_step_stride = a.noise_step_stride;
+    p.noise_batch_stride = a.const_noise ? 0 : static_cast<long long>(JF) * T;
+    p.B = B; p.S = S; p.T = T; p.J = JF; p.mode = a.mode;
+    p.clip_denoised = a.clip;
+    TRY((launch_gemm<96, EpiOutStep>(e->m_g16, e->m_wout, e->MB, e->N_out_pad, 3 * d, p, s, e->num_sms)));
+    ++nk;
+  }
+  *n_kernels = nk;
+  return B200MDM_OK;
+}
+
+static int check_ready(b200mdm_engine* e, bool need_sched) {
+  if (!e) return fail(B200MDM_EINVAL, "null engine");
+  if (!e->finalized) return fail(B200MDM_ESTATE, "weights not finalised");
+  if (!e->cond_set) return fail(B200MDM_ESTATE, "b200mdm_set_cond has not been called");
+  if (need_sched && e->n_steps <= 0) return fail(B200MDM_ESTATE, "b200mdm_set_schedule has not been called");
+  return B200MDM_OK;
+}
+
+extern "C" int b200mdm_denoise(b200mdm_engine* e, const float* x_dev, const int32_t* timesteps_host, float* out_dev,
+                               void* stream) {
+  TRY(check_ready(e, false));
+  if (!x_dev || !timesteps_host || !out_dev) return fail(B200MDM_EINVAL, "null tensor");
+  for (int b = 0; b < e->B; ++b)
+    if (timesteps_host[b] < 0 || timesteps_host[b] >= e->cfg.temb_rows)
+      return fail(B200MDM_EINVAL, "timestep %d outside the pre-embedded range [0, %d)", timesteps_host[b], e->cfg.temb_rows);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemcpyAsync(e->tvec, timesteps_host, e->B * sizeof(int), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));  // timesteps_host is caller memory
+  StepArgs a;
+  a.mode = B200MDM_MODE_X0;
+  a.x_in = x_dev;
+  a.x_out = out_dev;
+  a.explicit_t = true;
+  int nk = 0;
+  TRY(enqueue_forward(e, a, s, &nk));
+  e->launches += nk;
+  return B200MDM_OK;
+}
+
+extern "C" int b200mdm_sample_step(b200mdm_engine* e, int32_t mode, int32_t index, const float* x_t_dev,
+                                   const float* noise_dev, int32_t flags, float* x_out_dev,
+                                   float* pred_xstart_dev, void* stream) {
+  TRY(check_ready(e, true));
+  if (mode != B200MDM_MODE_DDPM && mode != B200MDM_MODE_DDIM) return fail(B200MDM_EINVAL, "bad mode");
+  if (index < 0 || index >= e->n_steps) return fail(B200MDM_EINVAL, "schedule index out of range");
+  if (!x_t_dev || !noise_dev || !x_out_dev) return fail(B200MDM_EINVAL, "null tensor");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  step_set_kernel<<<1, 1, 0, s>>>(e->state, 0, index);
+  CUDA_TRY(cudaGetLastError());
+  StepArgs a;
+  a.mode = mode;
+  a.x_in = x_t_dev;
+  a.noise = noise_dev;
+  a.const_noise = flags & B200MDM_FLAG_CONST_NOISE;
+  a.clip = (flags & B200MDM_FLAG_CLIP_DENOISED) ? 1 : 0;
+  a.x_out = x_out_dev;
+  a.pred = pred_xstart_dev;
+  int nk = 0;
+  TRY(enqueue_forward(e, a, s, &nk));
+  e->launches += nk + 1;
+  return B200MDM_OK;
+}
+
+extern "C" int b200mdm_sample_loop(b200mdm_engine* e, int32_t mode, int32_t skip_timesteps, float* x_dev,
+                                   const float* noise_tape_dev, int64_t noise_step_stride, int32_t flags,
+                                   float* pred_xstart_dev, int32_t use_graph, void* stream) {
+  const int const_noise = flags & B200MDM_FLAG_CONST_NOISE;
+  TRY(check_ready(e, true));
+  if (mode != B200MDM_MODE_DDPM && mode != B200MDM_MODE_DDIM) return fail(B200MDM_EINVAL, "bad mode");
+  if (skip_timesteps < 0 || skip_timesteps >= e->n_steps) return fail(B200MDM_EINVAL, "bad skip_timesteps");
+  if (!x_dev || !noise_tape_dev) return fail(B200MDM_EINVAL, "null tensor");
+  cudaStream_t user = static_cast<cudaStream_t>(stream);
+  const int n_run = e->n_steps - skip_timesteps;
+  StepArgs a;
+  a.mode = mode;
+  a.x_in = x_dev;
+  a.x_out = x_dev;  // in place: every element is read and written by the same thread of the fused epilogue
+  a.noise = noise_tape_dev;
+  a.noise_step_stride = noise_step_stride;
+  a.const_noise = const_noise;
+  a.clip = (flags & B200MDM_FLAG_CLIP_DENOISED) ? 1 : 0;
+  a.pred = pred_xstart_dev;
+
+  if (!use_graph) {
+    step_set_kernel<<<1, 1, 0, user>>>(e->state, 0, n_run - 1);
+    CUDA_TRY(cudaGetLastError());
+    for (int k = 0; k < n_run; ++k) {
+      int nk = 0;
+      TRY(enqueue_forward(e, a, user, &nk));
+      step_advance_kernel<<<1, 1, 0, user>>>(e->state);
+      CUDA_TRY(cudaGetLastError());
+      e->launches += nk + 1;
+    }
+    e->launches += 1;
+    return B200MDM_OK;
+  }
+
+  // graph path: runs on the engine's own stream (the caller's may be the legacy default stream, which cannot
+  // be captured), ordered after / before the caller's stream with events.
+  GraphKey key;
+  key.mode = mode; key.B = e->B; key.T = e->T; key.const_noise = flags; key.x = x_dev;
+  key.noise = noise_tape_dev; key.pred = pred_xstart_dev; key.imask = e->inpaint_mask; key.imotion = e->inpaint_motion;
+  key.stride = noise_step_stride;
+  if (!e->graph_exec || !(key == e->graph_key)) {
+    drop_graph(e);
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(e->work, cudaStreamCaptureModeThreadLocal));
+    int nk = 0;
+    int r = enqueue_forward(e, a, e->work, &nk);
+    if (r == B200MDM_OK) {
+      step_advance_kernel<<<1, 1, 0, e->work>>>(e->state);
+      if (cudaGetLastError() != cudaSuccess) r = fail(B200MDM_ECUDA, "step_advance launch failed during capture");
+    }
+    cudaError_t ce = cudaStreamEndCapture(e->work, &graph);
+    if (r != B200MDM_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return r;
+    }
+    if (ce != cudaSuccess) return fail(B200MDM_ECUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+      e->graph_exec = nullptr;
+      return fail(B200MDM_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+    }
+    e->graph_key = key;
+    e->graph_kernels = nk + 1;
+  }
+  CUDA_TRY(cudaEventRecord(e->ev_in, user));
+  CUDA_TRY(cudaStreamWaitEvent(e->work, e->ev_in, 0));
+  step_set_kernel<<<1, 1, 0, e->work>>>(e->state, 0, n_run - 1);
+  CUDA_TRY(cudaGetLastError());
+  for (int k = 0; k < n_run; ++k) CUDA_TRY(cudaGraphLaunch(e->graph_exec, e->work));
+  CUDA_TRY(cudaEventRecord(e->ev_out, e->work));
+  CUDA_TRY(cudaStreamWaitEvent(user, e->ev_out, 0));
+  e->launches += 1 + static_cast<long long>(n_run) * e->graph_kernels;
+  return B200MDM_OK;
+}
+
+extern "C" int b200mdm_q_sample(b200mdm_engine* e, float sqrt_ac, float sqrt_1mac, const float* x_start_dev,
+                                const float* noise_dev, float* out_dev, int64_t n, void* stream) {
+  if (!e || !noise_dev || !out_dev || n <= 0) return fail(B200MDM_EINVAL, "bad argument");
+  q_sample_kernel<<<592, 256, 0, static_cast<cudaStream_t>(stream)>>>(out_dev, x_start_dev, noise_dev, sqrt_ac, sqrt_1mac,
+                                                                     static_cast<size_t>(n));
+  CUDA_TRY(cudaGetLastError());
+  e->launches++;
+  return B200MDM_OK;
+}
+
+extern "C" int64_t b200mdm_launch_count(b200mdm_engine* e, int32_t reset) {
+  if (!e) return 0;
+  long long v = e->launches;
+  if (reset) e->launches = 0;
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel tests
+template <int BN>
+static int test_gemm_bn(const void* a16, const void* w16, const float* bias, void* out16, int M, int N, int K, int act,
+                        cudaStream_t s, int sms) {
+  CUtensorMap ma, mb;
+  TRY(make_map(&ma, a16, M, K, K, GEMM_BLOCK_M));
+  TRY(make_map(&mb, w16, N, K, K, BN));
+  if (act) {
+    EpiBiasF16<true>::Params p{static_cast<__half*>(out16), bias, N};
+    return launch_gemm<BN, EpiBiasF16<true>>(ma, mb, M, N, K, p, s, sms);
+  }
+  EpiBiasF16<false>::Params p{static_cast<__half*>(out16), bias, N};
+  return launch_gemm<BN, EpiBiasF16<false>>(ma, mb, M, N, K, p, s, sms);
+}
+
+extern "C" int b200mdm_test_gemm_f16(const void* a16_dev, const void* w16_dev, const float* bias_dev, void* out16_dev,
+                                     int32_t M, int32_t N, int32_t K, int32_t act, int32_t block_n, void* stream) {
+  if (!a16_dev || !w16_dev || !bias_dev || !out16_dev || M <= 0 || N <= 0 || K <= 0 || K % 8 || N % 2)
+    return fail(B200MDM_EINVAL, "bad argument (K %% 8 == 0, N %% 2 == 0 required)");
+  TRY(init_kernel_attrs());
+  int dev = 0, sms = 148;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (block_n) {
+    case 256: return test_gemm_bn<256>(a16_dev, w16_dev, bias_dev, out16_dev, M, N, K, act, s, sms);
+    case 128: return test_gemm_bn<128>(a16_dev, w16_dev, bias_dev, out16_dev, M, N, K, act, s, sms);
+    case 96: return test_gemm_bn<96>(a16_dev, w16_dev, bias_dev, out16_dev, M, N, K, act, s, sms);
+    default: return fail(B200MDM_EINVAL, "block_n must be 256, 128 or 96");
+  }
+}
+
+extern "C" int b200mdm_test_attention(const void* qkv16_dev, void* out16_dev, const int32_t* kvlen_dev,
+                                      int32_t n_samples, int32_t S, int32_t d, void* stream) {
+  if (!qkv16_dev || !out16_dev || !kvlen_dev || n_samples <= 0 || S <= 0) return fail(B200MDM_EINVAL, "bad argument");
+  TRY(init_kernel_attrs());
+  return launch_attention(static_cast<const __half*>(qkv16_dev), static_cast<__half*>(out16_dev), kvlen_dev, n_samples, S,
+                          d, d / ATT_DH, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200mdm_test_layernorm(float* h32_dev, void* h16_dev, const float* gamma_dev, const float* beta_dev,
+                                      int32_t M, void* stream) {
+  if (!h32_dev || !h16_dev || !gamma_dev || !beta_dev || M <= 0) return fail(B200MDM_EINVAL, "bad argument");
+  return launch_layernorm(h32_dev, static_cast<__half*>(h16_dev), gamma_dev, beta_dev, M, static_cast<cudaStream_t>(stream));
+}

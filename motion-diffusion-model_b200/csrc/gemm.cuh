@@ -1,0 +1,182 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:   D[M,N] = A[M,K] * W[N,K]^T   (fp16 in, fp32 accumulate)
+//
+//   warp 0      : TMA producer  (cp.async.bulk.tensor 2-D, 128B-swizzled tiles, STAGES-deep mbarrier ring)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, kind::f16)
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue functor -> global)
+//
+// Two TMEM accumulator stages (2 x BLOCK_N fp32 columns) let the epilogue of tile i overlap the MMAs of tile
+// i+1.  Tiles are statically strided over the persistent grid (tile = blockIdx.x + k * gridDim.x, N fastest so
+// concurrently running CTAs share the same A rows in L2).  A is [M,K] row-major (K contiguous), W is the
+// torch nn.Linear layout [N,K] row-major -- both "K-major" UMMA operands, no transposes anywhere.
+// K tails / M tails / N tails rely on TMA out-of-bounds zero fill; the epilogue guards rows and columns.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;  // 64 fp16 = 128 B = one swizzle row
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 4;
+constexpr int GEMM_STG_FLOATS = 32 * 33;  // per-warp transpose scratch
+
+template <int BLOCK_N>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;  // 16 KB
+  static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STG_BYTES = GEMM_EPI_WARPS * GEMM_STG_FLOATS * 4;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int budget = 227 * 1024 - 1024 /*alignment slack*/ - STG_BYTES - BAR_BYTES;
+  static constexpr int STAGES = (budget / STAGE_BYTES) > 6 ? 6 : (budget / STAGE_BYTES);
+  static constexpr int TOTAL = 1024 + STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES;
+  static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
+};
+
+constexpr uint32_t tmem_cols_pow2(int n) { return n <= 32 ? 32u : n <= 64 ? 64u : n <= 128 ? 128u : n <= 256 ? 256u : 512u; }
+
+// Epi must provide:  struct Params;  and
+//   static __device__ void apply(const Params&, float (&v)[32], float* stg, int row0, int col0, int lane, int M, int N)
+// where thread `lane` holds accumulator row (row0 + lane), columns [col0, col0 + 32).
+template <int BLOCK_N, class Epi>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
+                 int K, typename Epi::Params ep) {
+  using SM = GemmSmem<BLOCK_N>;
+  constexpr int STAGES = SM::STAGES;
+  constexpr uint32_t ACC_STRIDE = (BLOCK_N <= 128) ? 128 : 256;      // TMEM columns between the two accumulators
+  constexpr uint32_t TMEM_COLS = tmem_cols_pow2(2 * ACC_STRIDE);
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N constraint (M=128)");
+  static_assert(BLOCK_N % 32 == 0, "epilogue works on 32-column chunks");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  float* stg_all = reinterpret_cast<float*>(smem + STAGES * SM::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES + SM::STG_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* acc_full = bars + 2 * STAGES;       // [2]
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_m = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], GEMM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = tiles + stage * SM::STAGE_BYTES;
+          uint8_t* sb = sa + SM::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], SM::STAGE_BYTES);
+          tma_load_2d(sa, &map_a, &full_bar[stage], kb * GEMM_BLOCK_K, m_blk * GEMM_BLOCK_M);
+          tma_load_2d(sb, &map_b, &full_bar[stage], kb * GEMM_BLOCK_K, n_blk * BLOCK_N);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(GEMM_BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&acc_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * ACC_STRIDE;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + stage * SM::STAGE_BYTES);
+          const uint32_t sb = sa + SM::A_BYTES;
+          const uint64_t da = umma_desc_k_sw128(sa);
+          const uint64_t db = umma_desc_k_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+            // advance 16 fp16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
+            umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[as]);  // accumulator complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    float* stg = stg_all + (warp - 2) * GEMM_STG_FLOATS;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      const int row0 = m_blk * GEMM_BLOCK_M + q * 32;
+      const uint32_t taddr = tmem_base + as * ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t raw[32];
+        tmem_ld_32x32(taddr + c, raw);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        if (c + 32 >= BLOCK_N) {
+          // last TMEM read of this accumulator is in registers: release it to the MMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+        const int col0 = n_blk * BLOCK_N + c;
+        if (row0 < M && col0 < N) Epi::apply(ep, v, stg, row0, col0, lane, M, N);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace b200

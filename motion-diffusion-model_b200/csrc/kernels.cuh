@@ -1,0 +1,214 @@
+// Small HBM/L2-bound kernels around the GEMMs: input packing (transpose + fp16 hi/lo split), per-step
+// conditioning token, LayerNorm rows, CFG blend of the hidden rows, weight repacking, table set-up.
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "epilogues.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------------------
+// x [B, JF, T] fp32 (reference layout, T contiguous)  ->  xin16 [B*S, ld] fp16 rows (b, s = 1 + t_off + t):
+//   columns [0,Kp) = hi, [Kp,2Kp) = lo, [2Kp,3Kp) = hi    (A' of the 3-pass split GEMM  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo)
+// Row s = 0 (conditioning token slot) and the pad columns stay zero from allocation time.
+__global__ void pack_input_kernel(const float* __restrict__ x, __half* __restrict__ xin, int B, int JF, int T, int S,
+                                  int Kp, int ld, int row_off) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int j0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int j = j0 + i, t = t0 + tx;
+    tile[i][tx] = (j < JF && t < T) ? x[(static_cast<size_t>(b) * JF + j) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, j = j0 + tx;
+    if (t < T && j < JF) {
+      const float v = tile[tx][i];
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      __half* dst = xin + (static_cast<size_t>(b) * S + row_off + t) * ld + j;
+      dst[0] = hi;
+      dst[Kp] = lo;
+      dst[2 * Kp] = hi;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tok0[b', :] = condproj[b', :] + temb_table[t(b'), :]      (reference model/mdm.py:195,218-220)
+//   t(b') = tvec[b' % B] when tvec != nullptr (model called with explicit timesteps), else timestep_map[state->cur]
+__global__ void tok0_kernel(float* __restrict__ tok0, const float* __restrict__ condproj,
+                            const float* __restrict__ temb_table, const int* __restrict__ tvec,
+                            const int* __restrict__ tmap, const StepState* __restrict__ state, int B, int d,
+                            int temb_rows) {
+  const int bp = blockIdx.x;
+  int t = (tvec != nullptr) ? tvec[bp % B] : tmap[state->cur];
+  t = min(max(t, 0), temb_rows - 1);
+  for (int c = threadIdx.x; c < d; c += blockDim.x)
+    tok0[static_cast<size_t>(bp) * d + c] = condproj[static_cast<size_t>(bp) * d + c] + temb_table[static_cast<size_t>(t) * d + c];
+}
+
+__global__ void step_advance_kernel(StepState* state) {
+  state->done += 1;
+  state->cur -= 1;
+}
+__global__ void step_set_kernel(StepState* state, int done, int cur) {
+  state->done = done;
+  state->cur = cur;
+  state->start = cur;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// In-place LayerNorm over rows of h32 [M, 512] (eps 1e-5, biased variance, two-pass like ATen) + fp16 copy.
+// One warp per row; 512 = 32 lanes x 4 float4.
+__global__ void layernorm512_kernel(float* __restrict__ h32, __half* __restrict__ h16, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, int M, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float4* p = reinterpret_cast<float4*>(h32 + static_cast<size_t>(row) * 512);
+  float4 v[4];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = p[lane + 32 * i];
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.f / 512.f);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    sq += (a * a + b * b) + (c * c + d * d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq * (1.f / 512.f) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  __half2* q = reinterpret_cast<__half2*>(h16 + static_cast<size_t>(row) * 512);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 g = g4[lane + 32 * i], be = b4[lane + 32 * i];
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + be.x;
+    o.y = (v[i].y - mean) * rstd * g.y + be.y;
+    o.z = (v[i].z - mean) * rstd * g.z + be.z;
+    o.w = (v[i].w - mean) * rstd * g.w + be.w;
+    p[lane + 32 * i] = o;
+    q[2 * (lane + 32 * i)] = __floats2half2_rn(o.x, o.y);
+    q[2 * (lane + 32 * i) + 1] = __floats2half2_rn(o.z, o.w);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CFG blend on the hidden rows + fp16 hi/lo split for the 3-pass output GEMM.
+//   v = h_u + scale[b] * (h_c - h_u)   (same expression as utils/sampler_util.py:34, applied before the linear
+//   OutputProcess: W(h_u + s(h_c-h_u)) + b == out_u + s(out_c - out_u) exactly in real arithmetic)
+//   halves == 1: v = h.       g16 row layout: [hi | lo | hi], ld = 3*d.
+__global__ void blend_split_kernel(const float* __restrict__ h32, __half* __restrict__ g16,
+                                   const float* __restrict__ scale, int B, int S, int d, int halves) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B * S) return;
+  const int b = row / S;
+  const float* hc = h32 + static_cast<size_t>(row) * d;
+  const float* hu = h32 + (static_cast<size_t>(B) * S + row) * d;
+  const float sc = (halves == 2) ? scale[b] : 0.f;
+  __half* dst = g16 + static_cast<size_t>(row) * 3 * d;
+  for (int c = lane * 2; c < d; c += 64) {
+    float2 a = *reinterpret_cast<const float2*>(hc + c);
+    if (halves == 2) {
+      const float2 u = *reinterpret_cast<const float2*>(hu + c);
+      a.x = __fadd_rn(u.x, __fmul_rn(sc, __fsub_rn(a.x, u.x)));
+      a.y = __fadd_rn(u.y, __fmul_rn(sc, __fsub_rn(a.y, u.y)));
+    }
+    const __half2 hi = __floats2half2_rn(a.x, a.y);
+    const float2 hif = __half22float2(hi);
+    const __half2 lo = __floats2half2_rn(a.x - hif.x, a.y - hif.y);
+    *reinterpret_cast<__half2*>(dst + c) = hi;
+    *reinterpret_cast<__half2*>(dst + d + c) = lo;
+    *reinterpret_cast<__half2*>(dst + 2 * d + c) = hi;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Weight repacking (one-time, at load).
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = __float2half_rn(src[i]);
+}
+// W [N, K] fp32 -> W' [Npad, 3*Kp] fp16 = [hi | hi | lo] (zero padding), partner of the [hi | lo | hi] activations.
+__global__ void split_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int N, int K, int Kp) {
+  const int n = blockIdx.x;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float v = w[static_cast<size_t>(n) * K + k];
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    __half* dst = out + static_cast<size_t>(n) * 3 * Kp + k;
+    dst[0] = hi;
+    dst[Kp] = hi;
+    dst[2 * Kp] = lo;
+  }
+}
+
+// y[r, c] = act( sum_k x[r, k] * w[c, k] + b[c] ), fp32, one warp per output element (tiny set-up GEMVs:
+// timestep-embedding MLP for every model timestep, text projection once per loop)
+template <int ACT>  // 0 none, 1 SiLU
+__global__ void small_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                    const float* __restrict__ b, float* __restrict__ y, int R, int C, int K,
+                                    int x_ld) {
+  const size_t widx = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (widx >= static_cast<size_t>(R) * C) return;
+  const int r = static_cast<int>(widx / C), c = static_cast<int>(widx % C);
+  const float* xr = x + static_cast<size_t>(r) * x_ld;
+  const float* wr = w + static_cast<size_t>(c) * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(xr[k], wr[k], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    acc += (b != nullptr) ? b[c] : 0.f;
+    if (ACT == 1) acc = acc / (1.f + expf(-acc));
+    y[static_cast<size_t>(r) * C + c] = acc;
+  }
+}
+
+// condproj rows for the packed batch: first B rows conditional, next B rows unconditional.
+//   text  : cond = (W clip + b) already in proj[B, d];  uncond = bias          (mask_cond zeros => bias only)
+//   action: cond = action_embedding[a[b]];              uncond = 0             (model/mdm.py:225-227)
+//   none  : 0
+__global__ void condproj_fill_kernel(float* __restrict__ condproj, const float* __restrict__ proj,
+                                     const float* __restrict__ bias, const float* __restrict__ action_emb,
+                                     const int* __restrict__ action, int B, int d, int rows, int first_uncond,
+                                     int cond_mode) {
+  const int bp = blockIdx.x;
+  if (bp >= rows) return;
+  const bool unc = first_uncond ? true : (bp >= B);
+  const int b = bp % B;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float v = 0.f;
+    if (cond_mode == 1) v = unc ? bias[c] : proj[static_cast<size_t>(b) * d + c];
+    else if (cond_mode == 2) v = unc ? 0.f : action_emb[static_cast<size_t>(action[b]) * d + c];
+    condproj[static_cast<size_t>(bp) * d + c] = v;
+  }
+}
+
+// x_t = sqrt_ac * x0 + sqrt_1mac * noise   (q_sample, diffusion/gaussian_diffusion.py:226-244)
+__global__ void q_sample_kernel(float* __restrict__ out, const float* __restrict__ x0, const float* __restrict__ noise,
+                                float a, float b, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float s = (x0 != nullptr) ? x0[i] : 0.f;
+    out[i] = __fadd_rn(__fmul_rn(a, s), __fmul_rn(b, noise[i]));
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,174 @@
+"""Thin Python wrapper over the C ABI (include/b200mdm.h): torch tensors in, torch tensors out.
+
+Everything numeric happens inside libb200mdm.so; this module only marshals pointers, keeps the tensors that
+the engine references alive, and canonicalises the reference's untyped ``y`` dict into the POD arguments of
+``b200mdm_set_cond``.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    """One engine per model instance (weights + workspace live on the current CUDA device)."""
+
+    def __init__(self, *, arch, latent_dim, ff_size, num_layers, num_heads, njoints, nfeats, cond_mode, cond_dim,
+                 num_actions, mask_frames, pos_embed_max_len, temb_rows):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("b200mdm needs a CUDA device (sm_100a); there is no CPU fallback")
+        cm = _lib.COND_TEXT if "text" in cond_mode else _lib.COND_ACTION if "action" in cond_mode else _lib.COND_NONE
+        self.cfg = _lib.Config(arch=_lib.ARCH[arch], latent_dim=latent_dim, ff_size=ff_size, num_layers=num_layers,
+                               num_heads=num_heads, njoints=njoints, nfeats=nfeats, cond_mode=cm, cond_dim=cond_dim,
+                               num_actions=num_actions, mask_frames=int(bool(mask_frames)),
+                               pos_embed_max_len=pos_embed_max_len, temb_rows=temb_rows)
+        h = ctypes.c_void_p()
+        check(self.lib.b200mdm_create(ctypes.byref(self.cfg), ctypes.byref(h)))
+        self.h = h
+        self.cond_mode = cm
+        self._keep = {}
+        self._cond_key = None
+        self._sched_key = None
+        self.batch = self.nframes = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200mdm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, sd):
+        for name, t in sd.items():
+            if not torch.is_tensor(t):
+                continue
+            t = t.detach().to(torch.float32).contiguous()
+            shape = (ctypes.c_int64 * t.dim())(*t.shape)
+            check(self.lib.b200mdm_load_weight(self.h, name.encode(), _ptr(t), shape, t.dim()))
+        check(self.lib.b200mdm_finalize_weights(self.h, _stream()))
+        self._cond_key = None
+
+    # ------------------------------------------------------------------ schedule
+    def set_schedule(self, rows, timestep_map, key=None):
+        if key is not None and key == self._sched_key:
+            return
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        tmap = np.ascontiguousarray(timestep_map, dtype=np.int32)
+        assert rows.shape == (len(tmap), _lib.SCHED_STRIDE)
+        check(self.lib.b200mdm_set_schedule(self.h, len(tmap), rows.ctypes.data_as(ctypes.c_void_p),
+                                            tmap.ctypes.data_as(ctypes.c_void_p)))
+        self._sched_key = key
+
+    # ------------------------------------------------------------------ conditioning
+    def set_cond(self, batch, nframes, y, guided, device):
+        """Canonicalise model_kwargs['y'] (data_loaders/tensors.py:22-64 schema).  `guided` => CFG pair."""
+        text_embed = y.get("text_embed") if y is not None else None
+        if isinstance(text_embed, tuple):
+            raise NotImplementedError("BERT (tokens, mask) conditioning belongs to the trans_dec path")
+        lengths = y.get("lengths") if y is not None else None
+        mask = y.get("mask") if y is not None else None
+        if mask is not None and mask.shape[-1] <= 1:      # model/mdm.py:242 "is_valid_mask"
+            lengths = None
+        elif lengths is None and mask is not None:        # prefix mask -> lengths (tensors.py:3-6)
+            lengths = mask.reshape(mask.shape[0], -1).sum(-1)
+        scale = y.get("scale") if (guided and y is not None) else None
+        if guided and scale is None:
+            raise AssertionError("ClassifierFreeSampleModel needs y['scale'] (sampler_util.py:34)")
+        uncond = bool(y.get("uncond", False)) if y is not None else False
+        action = y.get("action") if y is not None else None
+        key = (batch, nframes, guided, uncond,
+               None if text_embed is None else (text_embed.data_ptr(), text_embed._version),
+               None if lengths is None else tuple(int(v) for v in lengths.reshape(-1).tolist()),
+               None if scale is None else (scale.data_ptr(), scale._version),
+               None if action is None else tuple(int(v) for v in action.reshape(-1).tolist()))
+        if key == self._cond_key:
+            return
+        te = None
+        if text_embed is not None and self.cond_mode == _lib.COND_TEXT:
+            te = text_embed.detach().to(device=device, dtype=torch.float32)
+            te = te.reshape(-1, te.shape[-1])
+            if te.shape[0] == 1 and batch > 1:             # single prompt for the whole batch (sample/predict.py)
+                te = te.expand(batch, -1)
+            te = te.contiguous()
+            assert te.shape == (batch, self.cfg.cond_dim), (te.shape, batch, self.cfg.cond_dim)
+        ln = None
+        if lengths is not None:
+            ln = np.ascontiguousarray(lengths.detach().reshape(-1).cpu().numpy().astype(np.int64))
+            assert ln.shape[0] == batch
+        sc = None
+        if scale is not None:
+            sc = scale.detach().to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+            assert sc.shape[0] == batch
+        ac = None
+        if action is not None and self.cond_mode == _lib.COND_ACTION:
+            ac = np.ascontiguousarray(action.detach().reshape(batch, -1)[:, 0].cpu().numpy().astype(np.int64))
+        check(self.lib.b200mdm_set_cond(self.h, batch, nframes, _ptr(te),
+                                        None if ln is None else ln.ctypes.data_as(ctypes.c_void_p), _ptr(sc),
+                                        int(uncond), None if ac is None else ac.ctypes.data_as(ctypes.c_void_p),
+                                        _stream()))
+        self._keep["cond"] = (te, sc)
+        self._cond_key = key
+        self.batch, self.nframes = batch, nframes
+
+    def set_inpaint(self, mask, motion):
+        if mask is None:
+            check(self.lib.b200mdm_set_inpaint(self.h, None, None))
+            self._keep.pop("inpaint", None)
+            return
+        m8 = mask.to(torch.uint8).contiguous()
+        mo = motion.to(torch.float32).contiguous()
+        check(self.lib.b200mdm_set_inpaint(self.h, _ptr(m8), _ptr(mo)))
+        self._keep["inpaint"] = (m8, mo)
+
+    # ------------------------------------------------------------------ compute
+    def denoise(self, x, timesteps):
+        x = x.to(torch.float32).contiguous()
+        ts = np.ascontiguousarray(timesteps.detach().reshape(-1).cpu().numpy().astype(np.int32))
+        assert ts.shape[0] == x.shape[0]
+        out = torch.empty_like(x)
+        check(self.lib.b200mdm_denoise(self.h, _ptr(x), ts.ctypes.data_as(ctypes.c_void_p), _ptr(out), _stream()))
+        return out
+
+    def sample_step(self, mode, index, x_t, noise, flags=0, want_pred=True):
+        x_t = x_t.to(torch.float32).contiguous()
+        noise = noise.to(torch.float32).contiguous()
+        out = torch.empty_like(x_t)
+        pred = torch.empty_like(x_t) if want_pred else None
+        check(self.lib.b200mdm_sample_step(self.h, mode, index, _ptr(x_t), _ptr(noise), flags, _ptr(out), _ptr(pred),
+                                           _stream()))
+        return out, pred
+
+    def sample_loop(self, mode, x, tape, skip_timesteps=0, flags=0, use_graph=True, pred=None):
+        """x: [B,J,F,T] fp32 contiguous (x_T in, x_0 out, in place); tape: [n_run, B,J,F,T] (or [n_run,1,...])."""
+        assert x.is_contiguous() and tape.is_contiguous() and x.dtype == torch.float32 and tape.dtype == torch.float32
+        stride = tape.stride(0) if tape.shape[0] > 1 else 0
+        check(self.lib.b200mdm_sample_loop(self.h, mode, skip_timesteps, _ptr(x), _ptr(tape), stride, flags, _ptr(pred),
+                                           int(use_graph), _stream()))
+        self._keep["loop"] = (x, tape, pred)
+        return x
+
+    def q_sample(self, sqrt_ac, sqrt_1mac, x_start, noise):
+        out = torch.empty_like(noise)
+        check(self.lib.b200mdm_q_sample(self.h, float(sqrt_ac), float(sqrt_1mac), _ptr(x_start), _ptr(noise), _ptr(out),
+                                        noise.numel(), _stream()))
+        return out
+
+    def launch_count(self, reset=False):
+        return int(self.lib.b200mdm_launch_count(self.h, int(reset)))

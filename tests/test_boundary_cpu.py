@@ -1,0 +1,74 @@
+"""CPU: host-side boundary -- the C-ABI library loads and exports every symbol include/b200mdm.h declares, the
+Python mirror keeps the reference's API surface, and the product refuses to run without a GPU (no fallback)."""
+import ctypes
+import os
+import re
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+import b200mdm
+from conftest import ROOT, default_args
+
+
+def test_header_symbols_exported():
+    from b200mdm import _lib
+    hdr = open(os.path.join(ROOT, "include", "b200mdm.h")).read()
+    declared = sorted(set(re.findall(r"\b(b200mdm_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared, "no declarations parsed"
+    assert sorted(_lib.SYMBOLS) == declared
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.b200mdm_version() >= 1
+    assert ctypes.sizeof(_lib.Config) == 20 * 4
+
+
+def test_api_surface_matches_reference():
+    args = default_args(layers=2)
+    model, diffusion = b200mdm.create_model_and_diffusion(args, SimpleNamespace(dataset=SimpleNamespace()))
+    # attributes the reference's callers read (sample/generate.py:95-98,161-171; sampler_util.py:16-25)
+    for a in ["njoints", "nfeats", "data_rep", "cond_mode", "cond_mask_prob", "translation", "rot2xyz", "encode_text",
+              "text_encoder_type", "all_goal_joint_names", "parameters", "to", "eval", "train"]:
+        assert hasattr(model, a), a
+    assert (model.njoints, model.nfeats, model.data_rep, model.cond_mode) == (263, 1, "hml_vec", "text")
+    for a in ["num_timesteps", "timestep_map", "original_num_steps", "betas", "alphas_cumprod", "posterior_variance",
+              "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2", "model_mean_type",
+              "model_var_type", "p_sample_loop", "p_sample_loop_progressive", "ddim_sample_loop",
+              "ddim_sample_loop_progressive", "p_sample", "ddim_sample", "q_sample"]:
+        assert hasattr(diffusion, a), a
+    assert diffusion.num_timesteps == 50 and diffusion.timestep_map == list(range(50))
+    # reference state_dict keys / shapes load through the reference-style loader
+    sd = b200mdm.synthetic_state_dict(num_layers=2)
+    assert set(sd) == set(model.state_dict())
+    for k, v in model.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    sd["sequence_pos_encoder.pe"] = torch.zeros(5000, 1, 512)
+    sd["embed_timestep.sequence_pos_encoder.pe"] = torch.zeros(5000, 1, 512)
+    b200mdm.load_model_wo_clip(model, sd)
+    assert torch.equal(model.state_dict()["output_process.poseFinal.bias"], sd["output_process.poseFinal.bias"])
+    with pytest.raises(AssertionError):
+        b200mdm.load_model_wo_clip(model, dict(sd, bogus=torch.zeros(1)))
+    cfg = b200mdm.ClassifierFreeSampleModel(model)
+    assert cfg.njoints == 263 and cfg.cond_mask_prob == 0.1 and cfg.all_goal_joint_names[0] == "pelvis"
+    m0, _ = b200mdm.create_model_and_diffusion(default_args(layers=1, cond_mask_prob=0.0), SimpleNamespace(dataset=SimpleNamespace()))
+    with pytest.raises(AssertionError):
+        b200mdm.ClassifierFreeSampleModel(m0)
+
+
+def test_unsupported_configs_raise():
+    for over in (dict(arch="gru"), dict(arch="trans_dec", text_encoder_type="bert")):
+        with pytest.raises(NotImplementedError):
+            b200mdm.create_model_and_diffusion(default_args(layers=1, **over), SimpleNamespace(dataset=SimpleNamespace()))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    model, diffusion = b200mdm.create_model_and_diffusion(default_args(layers=1), SimpleNamespace(dataset=SimpleNamespace()))
+    x = torch.zeros(1, 263, 1, 8)
+    y = {"text_embed": torch.zeros(1, 1, 512), "mask": torch.ones(1, 1, 1, 8, dtype=torch.bool), "lengths": torch.tensor([8])}
+    with pytest.raises(RuntimeError):
+        model(x, torch.zeros(1, dtype=torch.long), y=y)
+    with pytest.raises(RuntimeError):
+        diffusion.p_sample_loop(model, (1, 263, 1, 8), clip_denoised=False, model_kwargs={"y": y})
