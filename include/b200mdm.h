@@ -120,13 +120,14 @@ int b200mdm_sample_step(b200mdm_engine* e, int32_t mode, int32_t index, const fl
                         int32_t flags, float* x_out_dev, float* pred_xstart_dev, void* stream);
 
 /* p_sample_loop / ddim_sample_loop (gaussian_diffusion.py:591-727 / 876-990) without returning to the host:
- * steps index = n_steps-1-skip_timesteps ... 0 are enqueued on `stream` (one CUDA graph of a single step,
- * replayed, when use_graph != 0).  x_dev holds x_T on entry (after any q_sample of init_image) and x_0 on
- * exit (in place).  noise_tape_dev: eps for step k at noise_tape_dev + k*noise_step_stride elements
- * (k = 0 is the first executed step).  pred_xstart_dev may be NULL. */
-int b200mdm_sample_loop(b200mdm_engine* e, int32_t mode, int32_t skip_timesteps, float* x_dev,
-                        const float* noise_tape_dev, int64_t noise_step_stride, int32_t flags,
-                        float* pred_xstart_dev, int32_t use_graph, void* stream);
+ * steps index = n_steps-1-skip_timesteps ... 0 are enqueued (one CUDA graph of a single step, replayed, when
+ * use_graph != 0; the graph runs on an engine-owned stream ordered against `stream` with events).
+ * x_T_dev: the initial sample (after any q_sample of init_image), not modified; x_0_dev: result (may alias x_T_dev).
+ * noise_tape_dev: eps for the k-th executed step at noise_tape_dev + k*noise_step_stride elements.
+ * flags: B200MDM_FLAG_*.  The tape must stay alive until the work enqueued here has completed. */
+int b200mdm_sample_loop(b200mdm_engine* e, int32_t mode, int32_t skip_timesteps, const float* x_T_dev, float* x_0_dev,
+                        const float* noise_tape_dev, int64_t noise_step_stride, int32_t flags, int32_t use_graph,
+                        void* stream);
 
 /* q_sample (gaussian_diffusion.py:226-244) at schedule index `index`: out = sqrt_ac*x_start + sqrt_1mac*noise;
  * x_start_dev NULL => zeros (gaussian_diffusion.py:693-694).  sqrt_ac / sqrt_1mac are the fp32 table values. */

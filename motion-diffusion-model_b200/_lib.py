@@ -62,7 +62,7 @@ def load():
     lib.b200mdm_set_inpaint.argtypes = [vp, vp, vp]
     lib.b200mdm_denoise.argtypes = [vp, vp, vp, vp, vp]
     lib.b200mdm_sample_step.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, vp]
-    lib.b200mdm_sample_loop.argtypes = [vp, i32, i32, vp, vp, i64, i32, vp, i32, i32, vp]
+    lib.b200mdm_sample_loop.argtypes = [vp, i32, i32, vp, vp, vp, i64, i32, i32, vp]
     lib.b200mdm_q_sample.argtypes = [vp, f32, f32, vp, vp, vp, i64, vp]
     lib.b200mdm_launch_count.argtypes = [vp, i32]
     lib.b200mdm_launch_count.restype = i64

@@ -87,12 +87,11 @@ struct LayerW {
 };
 
 struct GraphKey {
-  int mode = -1, B = 0, T = 0, const_noise = 0;
-  const void *x = nullptr, *noise = nullptr, *pred = nullptr, *imask = nullptr, *imotion = nullptr;
-  long long stride = 0;
+  int mode = -1, B = 0, T = 0, flags = 0;
+  const void *pred = nullptr, *imask = nullptr, *imotion = nullptr;
   bool operator==(const GraphKey& o) const {
-    return mode == o.mode && B == o.B && T == o.T && const_noise == o.const_noise && x == o.x && noise == o.noise &&
-           pred == o.pred && imask == o.imask && imotion == o.imotion && stride == o.stride;
+    return mode == o.mode && B == o.B && T == o.T && flags == o.flags && pred == o.pred && imask == o.imask &&
+           imotion == o.imotion;
   }
 };
 
@@ -115,7 +114,7 @@ struct b200mdm_engine {
   // per-(B,T) workspace
   int B = 0, T = 0, S = 0, halves = 1, Bp = 0, M = 0, MB = 0;
   __half *xin16 = nullptr, *h16 = nullptr, *qkv16 = nullptr, *att16 = nullptr, *ffn16 = nullptr, *g16 = nullptr;
-  float *h32 = nullptr, *tok0 = nullptr, *condproj = nullptr, *proj = nullptr, *scale = nullptr;
+  float *h32 = nullptr, *tok0 = nullptr, *condproj = nullptr, *proj = nullptr, *scale = nullptr, *x_work = nullptr;
   int *kvlen = nullptr, *tvec = nullptr, *action = nullptr;
   StepState* state = nullptr;
   CUtensorMap m_xin, m_h16, m_att, m_ffn, m_g16;
@@ -236,7 +235,7 @@ extern "C" int b200mdm_create(const b200mdm_config* cfg, b200mdm_engine** out) {
 
 static void free_workspace(b200mdm_engine* e) {
   dfree(e->xin16); dfree(e->h16); dfree(e->qkv16); dfree(e->att16); dfree(e->ffn16); dfree(e->g16);
-  dfree(e->h32); dfree(e->tok0); dfree(e->condproj); dfree(e->proj); dfree(e->scale);
+  dfree(e->h32); dfree(e->tok0); dfree(e->condproj); dfree(e->proj); dfree(e->scale); dfree(e->x_work);
   dfree(e->kvlen); dfree(e->tvec); dfree(e->action);
   e->B = e->T = 0;
   e->cond_set = false;
@@ -445,6 +444,7 @@ static int build_workspace(b200mdm_engine* e, int B, int T, int halves) {
   TRY(dalloc(&e->condproj, static_cast<size_t>(Bp) * d, true));
   TRY(dalloc(&e->proj, static_cast<size_t>(B) * d, true));
   TRY(dalloc(&e->scale, B, true));
+  TRY(dalloc(&e->x_work, static_cast<size_t>(B) * e->JF * T));
   TRY(dalloc(&e->kvlen, Bp));
   TRY(dalloc(&e->tvec, B, true));
   TRY(dalloc(&e->action, B, true));
@@ -526,8 +526,7 @@ extern "C" int b200mdm_set_inpaint(b200mdm_engine* e, const uint8_t* mask_dev, c
 struct StepArgs {
   int mode = B200MDM_MODE_X0;
   const float* x_in = nullptr;    // [B, JF, T] input to the denoiser (x_t)
-  const float* noise = nullptr;
-  long long noise_step_stride = 0;
+  const float* noise = nullptr;   // explicit eps (single step); nullptr => tape from the device step state
   int const_noise = 0;
   int clip = 0;
   float* x_out = nullptr;
@@ -591,7 +590,6 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
     p.inpaint_motion = e->inpaint_motion;
     p.sched = e->sched;
     p.state = e->state;
-    p.noise_step_stride = a.noise_step_stride;
     p.noise_batch_stride = a.const_noise ? 0 : static_cast<long long>(JF) * T;
     p.B = B; p.S = S; p.T = T; p.J = JF; p.mode = a.mode;
     p.clip_denoised = a.clip;
@@ -639,7 +637,7 @@ extern "C" int b200mdm_sample_step(b200mdm_engine* e, int32_t mode, int32_t inde
   if (index < 0 || index >= e->n_steps) return fail(B200MDM_EINVAL, "schedule index out of range");
   if (!x_t_dev || !noise_dev || !x_out_dev) return fail(B200MDM_EINVAL, "null tensor");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  step_set_kernel<<<1, 1, 0, s>>>(e->state, 0, index);
+  step_set_kernel<<<1, 1, 0, s>>>(e->state, 0, index, nullptr, 0);
   CUDA_TRY(cudaGetLastError());
   StepArgs a;
   a.mode = mode;
@@ -655,79 +653,82 @@ extern "C" int b200mdm_sample_step(b200mdm_engine* e, int32_t mode, int32_t inde
   return B200MDM_OK;
 }
 
-extern "C" int b200mdm_sample_loop(b200mdm_engine* e, int32_t mode, int32_t skip_timesteps, float* x_dev,
-                                   const float* noise_tape_dev, int64_t noise_step_stride, int32_t flags,
-                                   float* pred_xstart_dev, int32_t use_graph, void* stream) {
-  const int const_noise = flags & B200MDM_FLAG_CONST_NOISE;
+extern "C" int b200mdm_sample_loop(b200mdm_engine* e, int32_t mode, int32_t skip_timesteps, const float* x_T_dev,
+                                   float* x_0_dev, const float* noise_tape_dev, int64_t noise_step_stride,
+                                   int32_t flags, int32_t use_graph, void* stream) {
   TRY(check_ready(e, true));
   if (mode != B200MDM_MODE_DDPM && mode != B200MDM_MODE_DDIM) return fail(B200MDM_EINVAL, "bad mode");
   if (skip_timesteps < 0 || skip_timesteps >= e->n_steps) return fail(B200MDM_EINVAL, "bad skip_timesteps");
-  if (!x_dev || !noise_tape_dev) return fail(B200MDM_EINVAL, "null tensor");
+  if (!x_T_dev || !x_0_dev || !noise_tape_dev) return fail(B200MDM_EINVAL, "null tensor");
   cudaStream_t user = static_cast<cudaStream_t>(stream);
   const int n_run = e->n_steps - skip_timesteps;
+  const size_t x_bytes = static_cast<size_t>(e->B) * e->JF * e->T * sizeof(float);
+  // The loop runs in place on an engine-owned buffer (fixed address => the captured step graph never changes);
+  // every element is read and written by the same thread of the fused output epilogue.
   StepArgs a;
   a.mode = mode;
-  a.x_in = x_dev;
-  a.x_out = x_dev;  // in place: every element is read and written by the same thread of the fused epilogue
-  a.noise = noise_tape_dev;
-  a.noise_step_stride = noise_step_stride;
-  a.const_noise = const_noise;
+  a.x_in = e->x_work;
+  a.x_out = e->x_work;
+  a.noise = nullptr;
+  a.const_noise = flags & B200MDM_FLAG_CONST_NOISE;
   a.clip = (flags & B200MDM_FLAG_CLIP_DENOISED) ? 1 : 0;
-  a.pred = pred_xstart_dev;
 
-  if (!use_graph) {
-    step_set_kernel<<<1, 1, 0, user>>>(e->state, 0, n_run - 1);
-    CUDA_TRY(cudaGetLastError());
+  // The graph path runs on the engine's own stream (the caller's may be the legacy default stream, which cannot be
+  // captured), ordered after / before the caller's stream with events.
+  cudaStream_t s = use_graph ? e->work : user;
+  if (use_graph) {
+    GraphKey key;
+    key.mode = mode; key.B = e->B; key.T = e->T; key.flags = flags;
+    key.imask = e->inpaint_mask; key.imotion = e->inpaint_motion;
+    if (!e->graph_exec || !(key == e->graph_key)) {
+      drop_graph(e);
+      cudaGraph_t graph = nullptr;
+      CUDA_TRY(cudaStreamBeginCapture(e->work, cudaStreamCaptureModeThreadLocal));
+      int nk = 0;
+      int r = enqueue_forward(e, a, e->work, &nk);
+      if (r == B200MDM_OK) {
+        step_advance_kernel<<<1, 1, 0, e->work>>>(e->state);
+        if (cudaGetLastError() != cudaSuccess) r = fail(B200MDM_ECUDA, "step_advance launch failed during capture");
+      }
+      cudaError_t ce = cudaStreamEndCapture(e->work, &graph);
+      if (r != B200MDM_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return r;
+      }
+      if (ce != cudaSuccess) return fail(B200MDM_ECUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+      ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) {
+        e->graph_exec = nullptr;
+        return fail(B200MDM_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+      }
+      e->graph_key = key;
+      e->graph_kernels = nk + 1;
+    }
+    CUDA_TRY(cudaEventRecord(e->ev_in, user));
+    CUDA_TRY(cudaStreamWaitEvent(e->work, e->ev_in, 0));
+  }
+  CUDA_TRY(cudaMemcpyAsync(e->x_work, x_T_dev, x_bytes, cudaMemcpyDeviceToDevice, s));
+  step_set_kernel<<<1, 1, 0, s>>>(e->state, 0, n_run - 1, noise_tape_dev, noise_step_stride);
+  CUDA_TRY(cudaGetLastError());
+  e->launches += 1;
+  if (use_graph) {
+    for (int k = 0; k < n_run; ++k) CUDA_TRY(cudaGraphLaunch(e->graph_exec, s));
+    e->launches += static_cast<long long>(n_run) * e->graph_kernels;
+  } else {
     for (int k = 0; k < n_run; ++k) {
       int nk = 0;
-      TRY(enqueue_forward(e, a, user, &nk));
-      step_advance_kernel<<<1, 1, 0, user>>>(e->state);
+      TRY(enqueue_forward(e, a, s, &nk));
+      step_advance_kernel<<<1, 1, 0, s>>>(e->state);
       CUDA_TRY(cudaGetLastError());
       e->launches += nk + 1;
     }
-    e->launches += 1;
-    return B200MDM_OK;
   }
-
-  // graph path: runs on the engine's own stream (the caller's may be the legacy default stream, which cannot
-  // be captured), ordered after / before the caller's stream with events.
-  GraphKey key;
-  key.mode = mode; key.B = e->B; key.T = e->T; key.const_noise = flags; key.x = x_dev;
-  key.noise = noise_tape_dev; key.pred = pred_xstart_dev; key.imask = e->inpaint_mask; key.imotion = e->inpaint_motion;
-  key.stride = noise_step_stride;
-  if (!e->graph_exec || !(key == e->graph_key)) {
-    drop_graph(e);
-    cudaGraph_t graph = nullptr;
-    CUDA_TRY(cudaStreamBeginCapture(e->work, cudaStreamCaptureModeThreadLocal));
-    int nk = 0;
-    int r = enqueue_forward(e, a, e->work, &nk);
-    if (r == B200MDM_OK) {
-      step_advance_kernel<<<1, 1, 0, e->work>>>(e->state);
-      if (cudaGetLastError() != cudaSuccess) r = fail(B200MDM_ECUDA, "step_advance launch failed during capture");
-    }
-    cudaError_t ce = cudaStreamEndCapture(e->work, &graph);
-    if (r != B200MDM_OK) {
-      if (graph) cudaGraphDestroy(graph);
-      return r;
-    }
-    if (ce != cudaSuccess) return fail(B200MDM_ECUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-    ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ce != cudaSuccess) {
-      e->graph_exec = nullptr;
-      return fail(B200MDM_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
-    }
-    e->graph_key = key;
-    e->graph_kernels = nk + 1;
+  CUDA_TRY(cudaMemcpyAsync(x_0_dev, e->x_work, x_bytes, cudaMemcpyDeviceToDevice, s));
+  if (use_graph) {
+    CUDA_TRY(cudaEventRecord(e->ev_out, e->work));
+    CUDA_TRY(cudaStreamWaitEvent(user, e->ev_out, 0));
   }
-  CUDA_TRY(cudaEventRecord(e->ev_in, user));
-  CUDA_TRY(cudaStreamWaitEvent(e->work, e->ev_in, 0));
-  step_set_kernel<<<1, 1, 0, e->work>>>(e->state, 0, n_run - 1);
-  CUDA_TRY(cudaGetLastError());
-  for (int k = 0; k < n_run; ++k) CUDA_TRY(cudaGraphLaunch(e->graph_exec, e->work));
-  CUDA_TRY(cudaEventRecord(e->ev_out, e->work));
-  CUDA_TRY(cudaStreamWaitEvent(user, e->ev_out, 0));
-  e->launches += 1 + static_cast<long long>(n_run) * e->graph_kernels;
   return B200MDM_OK;
 }
 

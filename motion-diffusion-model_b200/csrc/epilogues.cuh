@@ -20,6 +20,8 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 
 // ---------------------------------------------------------------------------------------------------------
 // out16[row, col] = fp16( act(acc + bias[col]) )          (QKV projection, FFN up-projection)
+// Column phase: lane owns 8 adjacent columns (16 B of fp16) of one row; 4 lanes cover the 32 columns of a row,
+// so one warp-wide store writes 8 complete 64-B row segments and 4 passes cover the chunk.
 template <bool GELU>
 struct EpiBiasF16 {
   struct Params {
@@ -30,34 +32,46 @@ struct EpiBiasF16 {
   static __device__ __forceinline__ void apply(const Params& p, float (&v)[32], float* stg, int row0, int col0,
                                                int lane, int M, int N) {
     chunk_to_cols(v, stg, lane);
-    // two rows per pass: lanes 0-15 -> row rr, lanes 16-31 -> row rr+1; each lane owns 2 adjacent columns
-    const int c = (lane & 15) * 2;
+    const int c = (lane & 3) * 8;
     const int col = col0 + c;
-    const bool col_ok = col + 1 < N;  // N is even for every caller
-    float b0 = 0.f, b1 = 0.f;
-    if (col_ok) {
-      b0 = p.bias[col];
-      b1 = p.bias[col + 1];
-    }
-#pragma unroll 4
-    for (int rr = 0; rr < 32; rr += 2) {
-      const int r = rr + (lane >> 4);
+    const bool col_ok = col + 7 < N;
+    float b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = (col + j < N) ? p.bias[col + j] : 0.f;
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const int r = pass * 8 + (lane >> 2);
       const int row = row0 + r;
-      float x0 = stg[r * 33 + c] + b0;
-      float x1 = stg[r * 33 + c + 1] + b1;
-      if (GELU) {
-        x0 = gelu_erf(x0);
-        x1 = gelu_erf(x1);
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        x[j] = stg[r * 33 + c + j] + b[j];
+        if (GELU) x[j] = gelu_erf(x[j]);
       }
-      if (row < M && col_ok)
-        *reinterpret_cast<__half2*>(p.out + static_cast<size_t>(row) * p.ld + col) = __floats2half2_rn(x0, x1);
+      if (row < M) {
+        __half* dst = p.out + static_cast<size_t>(row) * p.ld + col;
+        if (col_ok) {
+          uint4 pk;
+          __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
+          __half2 h2 = __floats2half2_rn(x[4], x[5]), h3 = __floats2half2_rn(x[6], x[7]);
+          pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(dst) = pk;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (col + j < N) dst[j] = __float2half_rn(x[j]);
+        }
+      }
     }
   }
 };
 
 // ---------------------------------------------------------------------------------------------------------
 // h32[row, col] += acc + bias[col]      (attention out-projection / FFN down-projection + residual; the
-// LayerNorm that follows is a separate row kernel in this revision)
+// LayerNorm that follows is a separate row kernel in this revision).  Column phase: lane owns 4 adjacent columns
+// (one float4) of one row, 8 lanes cover a 128-B row segment, 8 passes cover the chunk; all 8 residual loads are
+// issued before the first use so that they are in flight together.
 struct EpiResidualF32 {
   struct Params {
     float* h32;
@@ -66,17 +80,29 @@ struct EpiResidualF32 {
   };
   static __device__ __forceinline__ void apply(const Params& p, float (&v)[32], float* stg, int row0, int col0,
                                                int lane, int M, int N) {
+    const int c = (lane & 7) * 4;
+    const int col = col0 + c;       // N % 4 == 0 for every caller (N = 512)
+    const int rsub = lane >> 3;
+    float4 res[8];
+    const bool col_ok = col + 3 < N;
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
+      const int row = row0 + pass * 4 + rsub;
+      res[pass] = (row < M && col_ok) ? *reinterpret_cast<const float4*>(p.h32 + static_cast<size_t>(row) * p.ld + col)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     chunk_to_cols(v, stg, lane);
-    const int col = col0 + lane;
-    if (col >= N) return;
-    const float b = p.bias[col];
-#pragma unroll 4
-    for (int rr = 0; rr < 32; ++rr) {
-      const int row = row0 + rr;
-      if (row < M) {
-        float* dst = p.h32 + static_cast<size_t>(row) * p.ld + col;
-        *dst = *dst + (stg[rr * 33 + lane] + b);
-      }
+    const float4 b = col_ok ? *reinterpret_cast<const float4*>(p.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
+      const int r = pass * 4 + rsub;
+      const int row = row0 + r;
+      float4 o;
+      o.x = res[pass].x + (stg[r * 33 + c + 0] + b.x);
+      o.y = res[pass].y + (stg[r * 33 + c + 1] + b.y);
+      o.z = res[pass].z + (stg[r * 33 + c + 2] + b.z);
+      o.w = res[pass].w + (stg[r * 33 + c + 3] + b.w);
+      if (row < M && col_ok) *reinterpret_cast<float4*>(p.h32 + static_cast<size_t>(row) * p.ld + col) = o;
     }
   }
 };
@@ -134,20 +160,21 @@ struct StepState {
   int cur;       // schedule index i of the step in flight
   int start;     // schedule index of the first step (num_timesteps - 1 - skip)
   int pad;
+  const float* noise;            // loop mode: base of the noise tape (set per loop, so the step graph is reusable)
+  long long noise_step_stride;   // loop mode: elements between consecutive steps of the tape
 };
 
 struct EpiOutStep {
   struct Params {
     const float* bias;        // [J]
     const float* x_t;         // [B, J, T]
-    const float* noise;       // base of the tape; step k at noise + k*noise_step_stride
+    const float* noise;       // explicit eps for one step; nullptr => tape described by *state (loop mode)
     float* x_out;             // [B, J, T]
     float* pred_xstart;       // nullable
     const unsigned char* inpaint_mask;  // nullable, bool [B, J, T]
     const float* inpaint_motion;        // [B, J, T]
     const float* sched;       // [n_steps, SCHED_STRIDE]
     const StepState* state;
-    long long noise_step_stride;   // elements between consecutive steps of the tape (0 => one buffer)
     long long noise_batch_stride;  // J*T normally, 0 for const_noise
     int B, S, T, J, mode;
     int clip_denoised;        // clamp x0 to [-1, 1] after the inpainting blend (gaussian_diffusion.py:348-352)
@@ -166,7 +193,7 @@ struct EpiOutStep {
       const float* row_s = p.sched + static_cast<size_t>(st.cur) * SCHED_STRIDE;
       c1 = row_s[0]; c2 = row_s[1]; sr = row_s[3]; srm1 = row_s[4]; sq = row_s[5]; ce = row_s[6];
       sg = (p.mode == 1) ? row_s[2] : row_s[7];
-      nz = p.noise + static_cast<long long>(st.done) * p.noise_step_stride +
+      nz = (p.noise != nullptr ? p.noise : st.noise + static_cast<long long>(st.done) * st.noise_step_stride) +
            static_cast<long long>(b) * p.noise_batch_stride;
     }
 #pragma unroll

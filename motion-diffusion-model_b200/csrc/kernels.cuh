@@ -55,10 +55,12 @@ __global__ void step_advance_kernel(StepState* state) {
   state->done += 1;
   state->cur -= 1;
 }
-__global__ void step_set_kernel(StepState* state, int done, int cur) {
+__global__ void step_set_kernel(StepState* state, int done, int cur, const float* noise, long long noise_step_stride) {
   state->done = done;
   state->cur = cur;
   state->start = cur;
+  state->noise = noise;
+  state->noise_step_stride = noise_step_stride;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -180,7 +180,7 @@ class GaussianDiffusion:
             img = eng.q_sample(np.float32(self.sqrt_alphas_cumprod[first]),
                                np.float32(self.sqrt_one_minus_alphas_cumprod[first]),
                                init_image.to(device=device, dtype=torch.float32).contiguous(), img.contiguous())
-        return img.contiguous().clone() if img is noise else img.contiguous()
+        return img.contiguous()
 
     @staticmethod
     def _draw_tape(n_run, img):

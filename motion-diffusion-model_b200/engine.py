@@ -93,13 +93,6 @@ class Engine:
             raise AssertionError("ClassifierFreeSampleModel needs y['scale'] (sampler_util.py:34)")
         uncond = bool(y.get("uncond", False)) if y is not None else False
         action = y.get("action") if y is not None else None
-        key = (batch, nframes, guided, uncond,
-               None if text_embed is None else (text_embed.data_ptr(), text_embed._version),
-               None if lengths is None else tuple(int(v) for v in lengths.reshape(-1).tolist()),
-               None if scale is None else (scale.data_ptr(), scale._version),
-               None if action is None else tuple(int(v) for v in action.reshape(-1).tolist()))
-        if key == self._cond_key:
-            return
         te = None
         if text_embed is not None and self.cond_mode == _lib.COND_TEXT:
             te = text_embed.detach().to(device=device, dtype=torch.float32)
@@ -124,7 +117,6 @@ class Engine:
                                         int(uncond), None if ac is None else ac.ctypes.data_as(ctypes.c_void_p),
                                         _stream()))
         self._keep["cond"] = (te, sc)
-        self._cond_key = key
         self.batch, self.nframes = batch, nframes
 
     def set_inpaint(self, mask, motion):
@@ -155,14 +147,17 @@ class Engine:
                                            _stream()))
         return out, pred
 
-    def sample_loop(self, mode, x, tape, skip_timesteps=0, flags=0, use_graph=True, pred=None):
-        """x: [B,J,F,T] fp32 contiguous (x_T in, x_0 out, in place); tape: [n_run, B,J,F,T] (or [n_run,1,...])."""
-        assert x.is_contiguous() and tape.is_contiguous() and x.dtype == torch.float32 and tape.dtype == torch.float32
-        stride = tape.stride(0) if tape.shape[0] > 1 else 0
-        check(self.lib.b200mdm_sample_loop(self.h, mode, skip_timesteps, _ptr(x), _ptr(tape), stride, flags, _ptr(pred),
-                                           int(use_graph), _stream()))
-        self._keep["loop"] = (x, tape, pred)
-        return x
+    def sample_loop(self, mode, x, tape, skip_timesteps=0, flags=0, use_graph=True):
+        """x: [B,J,F,T] fp32 (x_T, left untouched); tape: [n_run, B,J,F,T] fp32.  Returns x_0 (new tensor)."""
+        x = x.to(torch.float32).contiguous()
+        assert tape.is_contiguous() and tape.dtype == torch.float32
+        out = torch.empty_like(x)
+        check(self.lib.b200mdm_sample_loop(self.h, mode, skip_timesteps, _ptr(x), _ptr(out), _ptr(tape), tape.stride(0),
+                                           flags, int(use_graph), _stream()))
+        # the loop is asynchronous and runs on the engine stream: keep its inputs alive and tell the caching
+        # allocator that another stream is using them
+        self._keep["loop"] = (x, tape)
+        return out
 
     def q_sample(self, sqrt_ac, sqrt_1mac, x_start, noise):
         out = torch.empty_like(noise)

@@ -1,0 +1,85 @@
+"""GPU: each hand-written kernel against a plain torch fp32 restatement of the same op (through the C ABI)."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from b200mdm import _lib as L
+    return L, L.load()
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize("M,N,K,bn,act", [
+    (128, 256, 64, 256, 0),          # one tile, one k-block
+    (128, 256, 512, 256, 0),         # k pipeline wraps the 4-stage ring twice
+    (300, 512, 512, 256, 0),         # M tail (300 = 2*128 + 44), 2 N tiles
+    (25216 // 8, 1536, 512, 256, 0),  # QKV shape (M scaled down), many tiles per CTA -> both accumulator stages
+    (1000, 1024, 512, 256, 1),       # FFN up + exact GELU
+    (777, 512, 1024, 256, 0),        # FFN down shape
+    (394, 512, 792, 128, 0),         # embed GEMM: K = 3*264 (K tail: 792 = 12*64 + 24), BLOCK_N 128
+    (394, 288, 1536, 96, 0),         # output GEMM: BLOCK_N 96, N = 3 tiles
+    (394, 264, 1536, 96, 0),         # N tail inside the last 96-wide tile
+    (5, 16, 8, 96, 1),               # tiny
+])
+def test_gemm_tcgen05(M, N, K, bn, act):
+    L, lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = (torch.randn(M, K, device="cuda", generator=g)).half()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+    L.check(lib.b200mdm_test_gemm_f16(_p(a), _p(w), _p(bias), _p(out), M, N, K, act, bn, _stream()))
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias
+    if act:
+        ref = torch.nn.functional.gelu(ref)
+    err = (out.float() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all()
+    assert err < 4e-3 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("n,S,kv", [(3, 197, [197, 121, 58]), (2, 41, [41, 1]), (4, 61, [61, 46, 31, 2]), (1, 16, [16]),
+                                    (2, 33, [20, 33])])
+def test_attention(n, S, kv):
+    L, lib = _lib()
+    d, H, dh = 512, 4, 128
+    g = torch.Generator(device="cuda").manual_seed(S)
+    qkv = torch.randn(n * S, 3 * d, device="cuda", generator=g).half()
+    kvlen = torch.tensor(kv, device="cuda", dtype=torch.int32)
+    out = torch.full((n * S, d), float("nan"), device="cuda", dtype=torch.float16)
+    L.check(lib.b200mdm_test_attention(_p(qkv), _p(out), _p(kvlen), n, S, d, _stream()))
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().view(n, S, 3, H, dh).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / dh ** 0.5
+    mask = torch.arange(S, device="cuda")[None, :] >= kvlen[:, None]
+    s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(n * S, d)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("M", [1, 8, 1000, 25216 // 4 + 3])
+def test_layernorm(M):
+    L, lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(M)
+    x = torch.randn(M, 512, device="cuda", generator=g) * 3 + 0.5
+    gamma = torch.randn(512, device="cuda", generator=g)
+    beta = torch.randn(512, device="cuda", generator=g)
+    ref = torch.nn.functional.layer_norm(x, (512,), gamma, beta, 1e-5)
+    h32 = x.clone()
+    h16 = torch.empty(M, 512, device="cuda", dtype=torch.float16)
+    L.check(lib.b200mdm_test_layernorm(_p(h32), _p(h16), _p(gamma), _p(beta), M, _stream()))
+    torch.cuda.synchronize()
+    assert (h32 - ref).abs().max().item() < 2e-5
+    assert (h16.float() - ref).abs().max().item() < 4e-3
