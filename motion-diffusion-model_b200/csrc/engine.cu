@@ -59,18 +59,23 @@ static int resolve_driver() {
   return B200MDM_OK;
 }
 // fp16 matrix [rows, cols] with leading dimension ld (elements); box = box_rows x 64 columns, 128-byte swizzle.
-static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+// elem_bytes 2 = fp16, 4 = fp32; the box is always 128 bytes wide (64 fp16 / 32 fp32 columns) x box_rows.
+static int make_map_t(CUtensorMap* m, const void* ptr, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows) {
   TRY(resolve_driver());
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16) return fail(B200MDM_EINVAL, "TMA operand misaligned");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * elem_bytes) % 16) return fail(B200MDM_EINVAL, "TMA operand misaligned");
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstr[1] = {ld * 2};
-  cuuint32_t box[2] = {GEMM_BLOCK_K, box_rows};
+  cuuint64_t gstr[1] = {ld * elem_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = g_encode(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B200MDM_ECUDA, "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
   return B200MDM_OK;
+}
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  return make_map_t(m, ptr, 2, rows, cols, ld, box_rows);
 }
 
 // ------------------------------------------------------------------------------------------------ engine
@@ -117,7 +122,10 @@ struct b200mdm_engine {
   float *h32 = nullptr, *tok0 = nullptr, *condproj = nullptr, *proj = nullptr, *scale = nullptr, *x_work = nullptr;
   int *kvlen = nullptr, *tvec = nullptr, *action = nullptr;
   StepState* state = nullptr;
-  CUtensorMap m_xin, m_h16, m_att, m_ffn, m_g16;
+  CUtensorMap m_xin, m_h16, m_att, m_ffn, m_g16;      // A operands (loads, box 128 rows)
+  CUtensorMap m_qkv_st, m_ffn_st, m_h32_io;            // epilogue slabs (box 32 rows x 128 bytes)
+  CUtensorMap m_h32_c, m_h32_u, m_h16_c, m_h16_u;      // per-CFG-half views of h32 / h16 for the embedding epilogue
+  float* pe_bias = nullptr;
   bool cond_set = false;
   const unsigned char* inpaint_mask = nullptr;
   const float* inpaint_motion = nullptr;
@@ -146,7 +154,7 @@ static void dfree(T*& p) {
 template <int BN, class Epi>
 static int set_gemm_attr() {
   CUDA_TRY(cudaFuncSetAttribute(gemm_f16_tcgen05<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                GemmSmem<BN>::TOTAL));
+                                GemmSmem<BN, Epi>::TOTAL));
   return B200MDM_OK;
 }
 static int init_kernel_attrs() {
@@ -156,8 +164,6 @@ static int init_kernel_attrs() {
   TRY((set_gemm_attr<256, EpiBiasF16<true>>()));
   TRY((set_gemm_attr<128, EpiBiasF16<false>>()));
   TRY((set_gemm_attr<128, EpiBiasF16<true>>()));
-  TRY((set_gemm_attr<96, EpiBiasF16<false>>()));
-  TRY((set_gemm_attr<96, EpiBiasF16<true>>()));
   TRY((set_gemm_attr<256, EpiResidualF32>()));
   TRY((set_gemm_attr<128, EpiEmbed>()));
   TRY((set_gemm_attr<96, EpiOutStep>()));
@@ -167,11 +173,11 @@ static int init_kernel_attrs() {
 }
 
 template <int BN, class Epi>
-static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, int M, int N, int K, const typename Epi::Params& p,
-                       cudaStream_t s, int num_sms) {
+static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int M, int N, int K,
+                       const typename Epi::Params& p, cudaStream_t s, int num_sms) {
   const int tiles = ((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_f16_tcgen05<BN, Epi><<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, s>>>(a, b, M, N, K, p);
+  gemm_f16_tcgen05<BN, Epi><<<grid, GEMM_THREADS, GemmSmem<BN, Epi>::TOTAL, s>>>(a, b, c, M, N, K, p);
   CUDA_TRY(cudaGetLastError());
   return B200MDM_OK;
 }
@@ -235,7 +241,7 @@ extern "C" int b200mdm_create(const b200mdm_config* cfg, b200mdm_engine** out) {
 
 static void free_workspace(b200mdm_engine* e) {
   dfree(e->xin16); dfree(e->h16); dfree(e->qkv16); dfree(e->att16); dfree(e->ffn16); dfree(e->g16);
-  dfree(e->h32); dfree(e->tok0); dfree(e->condproj); dfree(e->proj); dfree(e->scale); dfree(e->x_work);
+  dfree(e->h32); dfree(e->tok0); dfree(e->condproj); dfree(e->proj); dfree(e->scale); dfree(e->x_work); dfree(e->pe_bias);
   dfree(e->kvlen); dfree(e->tvec); dfree(e->action);
   e->B = e->T = 0;
   e->cond_set = false;
@@ -455,6 +461,17 @@ static int build_workspace(b200mdm_engine* e, int B, int T, int halves) {
   TRY(make_map(&e->m_att, e->att16, M, d, d, GEMM_BLOCK_M));
   TRY(make_map(&e->m_ffn, e->ffn16, M, e->ff, e->ff, GEMM_BLOCK_M));
   TRY(make_map(&e->m_g16, e->g16, MB, 3 * d, 3 * d, GEMM_BLOCK_M));
+  TRY(make_map_t(&e->m_qkv_st, e->qkv16, 2, M, 3 * d, 3 * d, 32));
+  TRY(make_map_t(&e->m_ffn_st, e->ffn16, 2, M, e->ff, e->ff, 32));
+  TRY(make_map_t(&e->m_h32_io, e->h32, 4, M, d, d, 32));
+  TRY(make_map_t(&e->m_h32_c, e->h32, 4, MB, d, d, 32));
+  TRY(make_map_t(&e->m_h16_c, e->h16, 2, MB, d, d, 32));
+  TRY(make_map_t(&e->m_h32_u, e->h32 + (halves == 2 ? MB * d : 0), 4, MB, d, d, 32));
+  TRY(make_map_t(&e->m_h16_u, e->h16 + (halves == 2 ? MB * d : 0), 2, MB, d, d, 32));
+  TRY(dalloc(&e->pe_bias, static_cast<size_t>(S) * d));
+  pe_bias_kernel<<<S, 128>>>(e->pe_bias, e->pe, e->b_in, S, d);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaDeviceSynchronize());
   return B200MDM_OK;
 }
 
@@ -544,34 +561,37 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
     CUDA_TRY(cudaGetLastError());
     ++nk;
   }
-  tok0_kernel<<<e->Bp, 128, 0, s>>>(e->tok0, e->condproj, e->temb_table, a.explicit_t ? e->tvec : nullptr, e->tmap,
-                                    e->state, B, d, e->cfg.temb_rows);
-  CUDA_TRY(cudaGetLastError());
-  ++nk;
   {
-    EpiEmbed::Params p{e->h32, e->h16, e->b_in, e->pe, e->tok0, B, S, d, e->halves};
-    TRY((launch_gemm<128, EpiEmbed>(e->m_xin, e->m_win, e->MB, d, 3 * Kp, p, s, e->num_sms)));
+    EpiEmbed::Params p;
+    p.h32_c = e->m_h32_c; p.h32_u = e->m_h32_u; p.h16_c = e->m_h16_c; p.h16_u = e->m_h16_u;
+    p.pe_bias = e->pe_bias;
+    p.S = S; p.d = d; p.halves = e->halves;
+    TRY((launch_gemm<128, EpiEmbed>(e->m_xin, e->m_win, e->m_xin, e->MB, d, 3 * Kp, p, s, e->num_sms)));
     ++nk;
   }
+  tok0_rows_kernel<<<e->Bp, 128, 0, s>>>(e->h32, e->h16, e->condproj, e->temb_table, e->pe,
+                                         a.explicit_t ? e->tvec : nullptr, e->tmap, e->state, B, S, d, e->cfg.temb_rows);
+  CUDA_TRY(cudaGetLastError());
+  ++nk;
   for (int l = 0; l < e->L; ++l) {
     const LayerW& w = e->layers[l];
     {
-      EpiBiasF16<false>::Params p{e->qkv16, w.bqkv, 3 * d};
-      TRY((launch_gemm<256, EpiBiasF16<false>>(e->m_h16, w.m_wqkv, e->M, 3 * d, d, p, s, e->num_sms)));
+      EpiBiasF16<false>::Params p{w.bqkv};
+      TRY((launch_gemm<256, EpiBiasF16<false>>(e->m_h16, w.m_wqkv, e->m_qkv_st, e->M, 3 * d, d, p, s, e->num_sms)));
     }
     TRY(launch_attention(e->qkv16, e->att16, e->kvlen, e->Bp, S, d, e->H, s));
     {
-      EpiResidualF32::Params p{e->h32, w.bo, d};
-      TRY((launch_gemm<256, EpiResidualF32>(e->m_att, w.m_wo, e->M, d, d, p, s, e->num_sms)));
+      EpiResidualF32::Params p{w.bo};
+      TRY((launch_gemm<256, EpiResidualF32>(e->m_att, w.m_wo, e->m_h32_io, e->M, d, d, p, s, e->num_sms)));
     }
     TRY(launch_layernorm(e->h32, e->h16, w.g1, w.be1, e->M, s));
     {
-      EpiBiasF16<true>::Params p{e->ffn16, w.b1, ff};
-      TRY((launch_gemm<256, EpiBiasF16<true>>(e->m_h16, w.m_w1, e->M, ff, d, p, s, e->num_sms)));
+      EpiBiasF16<true>::Params p{w.b1};
+      TRY((launch_gemm<256, EpiBiasF16<true>>(e->m_h16, w.m_w1, e->m_ffn_st, e->M, ff, d, p, s, e->num_sms)));
     }
     {
-      EpiResidualF32::Params p{e->h32, w.b2, d};
-      TRY((launch_gemm<256, EpiResidualF32>(e->m_ffn, w.m_w2, e->M, d, ff, p, s, e->num_sms)));
+      EpiResidualF32::Params p{w.b2};
+      TRY((launch_gemm<256, EpiResidualF32>(e->m_ffn, w.m_w2, e->m_h32_io, e->M, d, ff, p, s, e->num_sms)));
     }
     TRY(launch_layernorm(e->h32, e->h16, w.g2, w.be2, e->M, s));
     nk += 7;
@@ -593,7 +613,7 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
     p.noise_batch_stride = a.const_noise ? 0 : static_cast<long long>(JF) * T;
     p.B = B; p.S = S; p.T = T; p.J = JF; p.mode = a.mode;
     p.clip_denoised = a.clip;
-    TRY((launch_gemm<96, EpiOutStep>(e->m_g16, e->m_wout, e->MB, e->N_out_pad, 3 * d, p, s, e->num_sms)));
+    TRY((launch_gemm<96, EpiOutStep>(e->m_g16, e->m_wout, e->m_g16, e->MB, e->N_out_pad, 3 * d, p, s, e->num_sms)));
     ++nk;
   }
   *n_kernels = nk;
@@ -753,21 +773,22 @@ extern "C" int64_t b200mdm_launch_count(b200mdm_engine* e, int32_t reset) {
 template <int BN>
 static int test_gemm_bn(const void* a16, const void* w16, const float* bias, void* out16, int M, int N, int K, int act,
                         cudaStream_t s, int sms) {
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mc;
   TRY(make_map(&ma, a16, M, K, K, GEMM_BLOCK_M));
   TRY(make_map(&mb, w16, N, K, K, BN));
+  TRY(make_map_t(&mc, out16, 2, M, N, N, 32));
   if (act) {
-    EpiBiasF16<true>::Params p{static_cast<__half*>(out16), bias, N};
-    return launch_gemm<BN, EpiBiasF16<true>>(ma, mb, M, N, K, p, s, sms);
+    EpiBiasF16<true>::Params p{bias};
+    return launch_gemm<BN, EpiBiasF16<true>>(ma, mb, mc, M, N, K, p, s, sms);
   }
-  EpiBiasF16<false>::Params p{static_cast<__half*>(out16), bias, N};
-  return launch_gemm<BN, EpiBiasF16<false>>(ma, mb, M, N, K, p, s, sms);
+  EpiBiasF16<false>::Params p{bias};
+  return launch_gemm<BN, EpiBiasF16<false>>(ma, mb, mc, M, N, K, p, s, sms);
 }
 
 extern "C" int b200mdm_test_gemm_f16(const void* a16_dev, const void* w16_dev, const float* bias_dev, void* out16_dev,
                                      int32_t M, int32_t N, int32_t K, int32_t act, int32_t block_n, void* stream) {
-  if (!a16_dev || !w16_dev || !bias_dev || !out16_dev || M <= 0 || N <= 0 || K <= 0 || K % 8 || N % 2)
-    return fail(B200MDM_EINVAL, "bad argument (K %% 8 == 0, N %% 2 == 0 required)");
+  if (!a16_dev || !w16_dev || !bias_dev || !out16_dev || M <= 0 || N <= 0 || K <= 0 || K % 8 || N % 8)
+    return fail(B200MDM_EINVAL, "bad argument (K %% 8 == 0, N %% 8 == 0 required)");
   TRY(init_kernel_attrs());
   int dev = 0, sms = 148;
   CUDA_TRY(cudaGetDevice(&dev));
@@ -776,8 +797,7 @@ extern "C" int b200mdm_test_gemm_f16(const void* a16_dev, const void* w16_dev, c
   switch (block_n) {
     case 256: return test_gemm_bn<256>(a16_dev, w16_dev, bias_dev, out16_dev, M, N, K, act, s, sms);
     case 128: return test_gemm_bn<128>(a16_dev, w16_dev, bias_dev, out16_dev, M, N, K, act, s, sms);
-    case 96: return test_gemm_bn<96>(a16_dev, w16_dev, bias_dev, out16_dev, M, N, K, act, s, sms);
-    default: return fail(B200MDM_EINVAL, "block_n must be 256, 128 or 96");
+    default: return fail(B200MDM_EINVAL, "block_n must be 256 or 128");
   }
 }
 

@@ -1,147 +1,223 @@
-// Fused GEMM epilogues.  Each functor receives one 32x32 accumulator chunk: thread `lane` of the warp holds
-// accumulator row (row0 + lane), columns [col0, col0 + 32) in v[].  Row-major outputs go through a warp-private
-// 32x33 shared-memory transpose so that global accesses are row-contiguous (one 128-B line per instruction);
-// feature-major outputs ([B, J, T], T contiguous) are written straight from registers because consecutive
-// accumulator rows are consecutive frames.
+// Fused GEMM epilogues (see gemm.cuh for the calling protocol).  Thread = accumulator row.
+//
+// Row-major outputs are written as 128-byte-per-row slabs (32 rows of the warp x 64 fp16 or 32 fp32 columns = 4 KB)
+// staged in warp-private shared memory in the TMA 128-byte swizzle and shipped with cp.async.bulk.tensor stores;
+// residual inputs arrive the same way with TMA loads.  No global load/store instruction is issued by these
+// epilogues except broadcast bias reads, and out-of-range rows / columns are clipped by the TMA unit.
+// Feature-major outputs ([B, J, T], T contiguous) are written straight from registers because consecutive
+// accumulator rows are consecutive frames (coalesced along T).
 #pragma once
 #include <cuda_fp16.h>
 
+#include "gemm.cuh"
+#include "ptx.cuh"
+
 namespace b200 {
 
-__device__ __forceinline__ void chunk_to_cols(const float (&v)[32], float* stg, int lane) {
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
-  __syncwarp();
+// byte offset of 16-byte chunk j (0..7) of row r inside a [32 x 128 B] slab with the TMA SWIZZLE_128B pattern
+__device__ __forceinline__ uint32_t slab_off(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
+
+// exact (erf) GELU, torch F.gelu default (reference model/mdm.py:80 activation="gelu"):  gelu(x) = x * Phi(x).
+// Phi(-t) = 2^q(t) with q a degree-6 minimax fit of log2(0.5*erfc(t/sqrt 2)) on [0, 5.5] (|Phi error| < 1.5e-7,
+// |gelu error| < 8e-7 over all x, checked against torch fp64 in tests); Phi(t) = 1 - Phi(-t).  11 FP32 ops + one
+// MUFU.EX2 instead of the ~25 of erff() -- the epilogue of the FFN up-projection runs 26 M of these per layer.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float t = fminf(fabsf(x), 5.5f);
+  float q = 1.9175331544829533e-05f;
+  q = fmaf(q, t, -0.0006586098461411893f);
+  q = fmaf(q, t, 0.007754423655569553f);
+  q = fmaf(q, t, -0.05296541005373001f);
+  q = fmaf(q, t, -0.4590602517127991f);
+  q = fmaf(q, t, -1.1511220932006836f);
+  q = fmaf(q, t, -0.9999997019767761f);
+  float a;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(q));
+  const float phi = (x >= 0.f) ? (1.0f - a) : a;
+  return x * phi;
 }
 
-// exact-erf GELU (torch F.gelu default, reference model/mdm.py:80 activation="gelu")
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // out16[row, col] = fp16( act(acc + bias[col]) )          (QKV projection, FFN up-projection)
-// Column phase: lane owns 8 adjacent columns (16 B of fp16) of one row; 4 lanes cover the 32 columns of a row,
-// so one warp-wide store writes 8 complete 64-B row segments and 4 passes cover the chunk.
+// Two 32-column chunks fill one 64-column (128-byte) slab; slabs are double-buffered.  map_c: fp16 [M, N],
+// box {64 cols, 32 rows}, SWIZZLE_128B.
 template <bool GELU>
 struct EpiBiasF16 {
+  static constexpr int SMEM_PER_WARP = 2 * 4096;
+  static constexpr bool RELEASE_EARLY = true;
   struct Params {
-    __half* out;
     const float* bias;
-    int ld;
   };
-  static __device__ __forceinline__ void apply(const Params& p, float (&v)[32], float* stg, int row0, int col0,
-                                               int lane, int M, int N) {
-    chunk_to_cols(v, stg, lane);
-    const int c = (lane & 3) * 8;
-    const int col = col0 + c;
-    const bool col_ok = col + 7 < N;
-    float b[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) b[j] = (col + j < N) ? p.bias[col + j] : 0.f;
-#pragma unroll
-    for (int pass = 0; pass < 4; ++pass) {
-      const int r = pass * 8 + (lane >> 2);
-      const int row = row0 + r;
-      float x[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        x[j] = stg[r * 33 + c + j] + b[j];
-        if (GELU) x[j] = gelu_erf(x[j]);
-      }
-      if (row < M) {
-        __half* dst = p.out + static_cast<size_t>(row) * p.ld + col;
-        if (col_ok) {
-          uint4 pk;
-          __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
-          __half2 h2 = __floats2half2_rn(x[4], x[5]), h3 = __floats2half2_rn(x[6], x[7]);
-          pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-          pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-          *reinterpret_cast<uint4*>(dst) = pk;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (col + j < N) dst[j] = __float2half_rn(x[j]);
-        }
-      }
+  static __device__ __forceinline__ void tile_begin(EpiCtx&, const Params&, int, int) {}
+  static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0,
+                                               uint32_t) {
+    const int half = (col0 >> 5) & 1;
+    uint8_t* slab = ctx.smem + (ctx.seq & 1) * 4096;
+    if (half == 0) {
+      // the store issued two slabs ago read this buffer: make sure it has finished reading
+      if (ctx.lane == 0) bulk_wait_group_read<1>();
+      __syncwarp();
     }
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col0 + j + 3 < ctx.N) {
+        b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+      } else {
+        if (col0 + j + 0 < ctx.N) b.x = p.bias[col0 + j + 0];
+        if (col0 + j + 1 < ctx.N) b.y = p.bias[col0 + j + 1];
+        if (col0 + j + 2 < ctx.N) b.z = p.bias[col0 + j + 2];
+      }
+      float x0 = __uint_as_float(raw[j + 0]) + b.x, x1 = __uint_as_float(raw[j + 1]) + b.y;
+      float x2 = __uint_as_float(raw[j + 2]) + b.z, x3 = __uint_as_float(raw[j + 3]) + b.w;
+      if (GELU) {
+        x0 = gelu_erf(x0); x1 = gelu_erf(x1); x2 = gelu_erf(x2); x3 = gelu_erf(x3);
+      }
+      pk[j / 2] = pack_half2(x0, x1);
+      pk[j / 2 + 1] = pack_half2(x2, x3);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(slab + slab_off(ctx.lane, half * 4 + j)) =
+          make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    if (half == 1 || col0 + 32 >= ctx.N) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (ctx.lane == 0) {
+        tma_store_2d(ctx.map_c, slab, col0 - 32 * half, row0);
+        bulk_commit_group();
+      }
+      ctx.seq++;
+    }
+  }
+  static __device__ __forceinline__ void tile_end(EpiCtx&, const Params&, int, int, uint32_t) {}
+  static __device__ __forceinline__ void finish(EpiCtx& ctx) {
+    if (ctx.lane == 0) bulk_wait_group<0>();
+    __syncwarp();
   }
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// h32[row, col] += acc + bias[col]      (attention out-projection / FFN down-projection + residual; the
-// LayerNorm that follows is a separate row kernel in this revision).  Column phase: lane owns 4 adjacent columns
-// (one float4) of one row, 8 lanes cover a 128-B row segment, 8 passes cover the chunk; all 8 residual loads are
-// issued before the first use so that they are in flight together.
+// h32[row, col] += acc + bias[col]      (attention out-projection / FFN down-projection + residual, in place).
+// Per 32-column chunk: TMA load of the residual slab (issued one chunk ahead, three rotating buffers), add in
+// registers, write back into the same slab, TMA store.  map_c: fp32 [M, N], box {32 cols, 32 rows}, SWIZZLE_128B.
 struct EpiResidualF32 {
+  static constexpr int NBUF = 3;
+  static constexpr int SMEM_PER_WARP = NBUF * 4096;
+  static constexpr bool RELEASE_EARLY = true;
   struct Params {
-    float* h32;
     const float* bias;
-    int ld;
   };
-  static __device__ __forceinline__ void apply(const Params& p, float (&v)[32], float* stg, int row0, int col0,
-                                               int lane, int M, int N) {
-    const int c = (lane & 7) * 4;
-    const int col = col0 + c;       // N % 4 == 0 for every caller (N = 512)
-    const int rsub = lane >> 3;
-    float4 res[8];
-    const bool col_ok = col + 3 < N;
-#pragma unroll
-    for (int pass = 0; pass < 8; ++pass) {
-      const int row = row0 + pass * 4 + rsub;
-      res[pass] = (row < M && col_ok) ? *reinterpret_cast<const float4*>(p.h32 + static_cast<size_t>(row) * p.ld + col)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+  static __device__ __forceinline__ void prefetch(EpiCtx& ctx, uint32_t seq, int row0, int col0) {
+    // buffer seq % NBUF was last stored from NBUF chunks ago; only the most recent store may stay in flight
+    if (ctx.lane == 0) {
+      bulk_wait_group_read<1>();
+      const uint32_t b = seq % NBUF;
+      mbar_expect_tx(&ctx.bars[b], 4096);
+      tma_load_2d(ctx.smem + b * 4096, ctx.map_c, &ctx.bars[b], col0, row0);
     }
-    chunk_to_cols(v, stg, lane);
-    const float4 b = col_ok ? *reinterpret_cast<const float4*>(p.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  static __device__ __forceinline__ void tile_begin(EpiCtx& ctx, const Params&, int row0, int col_base) {
+    prefetch(ctx, ctx.seq, row0, col_base);
+  }
+  static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0,
+                                               uint32_t) {
+    const uint32_t b = ctx.seq % NBUF;
+    if (col0 + 32 < ctx.col_end && col0 + 32 < ctx.N) prefetch(ctx, ctx.seq + 1, row0, col0 + 32);
+    uint8_t* slab = ctx.smem + b * 4096;
+    mbar_wait(&ctx.bars[b], (ctx.seq / NBUF) & 1);
 #pragma unroll
-    for (int pass = 0; pass < 8; ++pass) {
-      const int r = pass * 4 + rsub;
-      const int row = row0 + r;
+    for (int j = 0; j < 8; ++j) {
+      float4* cell = reinterpret_cast<float4*>(slab + slab_off(ctx.lane, j));
+      const float4 r = *cell;
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
       float4 o;
-      o.x = res[pass].x + (stg[r * 33 + c + 0] + b.x);
-      o.y = res[pass].y + (stg[r * 33 + c + 1] + b.y);
-      o.z = res[pass].z + (stg[r * 33 + c + 2] + b.z);
-      o.w = res[pass].w + (stg[r * 33 + c + 3] + b.w);
-      if (row < M && col_ok) *reinterpret_cast<float4*>(p.h32 + static_cast<size_t>(row) * p.ld + col) = o;
+      o.x = r.x + (__uint_as_float(raw[4 * j + 0]) + bb.x);
+      o.y = r.y + (__uint_as_float(raw[4 * j + 1]) + bb.y);
+      o.z = r.z + (__uint_as_float(raw[4 * j + 2]) + bb.z);
+      o.w = r.w + (__uint_as_float(raw[4 * j + 3]) + bb.w);
+      *cell = o;
     }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (ctx.lane == 0) {
+      tma_store_2d(ctx.map_c, slab, col0, row0);
+      bulk_commit_group();
+    }
+    ctx.seq++;
+  }
+  static __device__ __forceinline__ void tile_end(EpiCtx&, const Params&, int, int, uint32_t) {}
+  static __device__ __forceinline__ void finish(EpiCtx& ctx) {
+    if (ctx.lane == 0) bulk_wait_group<0>();
+    __syncwarp();
   }
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// InputProcess + cond-token concat + positional encoding (reference model/mdm.py:238,251-252,343-349):
-//   GEMM rows are (b, s) over B*S; s == 0 is the conditioning token (taken from tok0, not from the GEMM),
-//   s >= 1 is frame s-1:  h = acc + bias + pe[s].  The frame rows are identical for the cond / uncond halves of
-//   the packed CFG batch, so each row is written `halves` times.
+// InputProcess + positional encoding (reference model/mdm.py:238,252,343-349):
+//   GEMM rows are (b, s) over B*S, s >= 1 is frame s-1:  h = acc + (bias + pe[s]).  The frame rows are identical for
+//   the cond / uncond halves of the packed CFG batch, so every slab is TMA-stored twice (one tensor map per half --
+//   the per-half maps also clip the rows of the last M tile that belong to the other half).  Row s == 0 (the
+//   conditioning token, mdm.py:251) is produced by tok0_rows_kernel right after this GEMM.
+//   Outputs: h32 (fp32 residual stream) and h16 (fp16 copy = next GEMM's A operand).
 struct EpiEmbed {
+  static constexpr int SMEM_PER_WARP = 4 * 4096;  // 2 fp32 slabs + 2 fp16 slabs
+  static constexpr bool RELEASE_EARLY = true;
   struct Params {
-    float* h32;
-    __half* h16;
-    const float* bias;   // [d]
-    const float* pe;     // [max_len, d]
-    const float* tok0;   // [halves*B, d]  = cond projection + timestep embedding (per step)
-    int B, S, d, halves;
+    CUtensorMap h32_c, h32_u, h16_c, h16_u;  // [B*S, d] views of the two halves, box 32 rows x 128 bytes
+    const float* pe_bias;                     // [S, d] = pe[s] + bias
+    int S, d, halves;
   };
-  static __device__ __forceinline__ void apply(const Params& p, float (&v)[32], float* stg, int row0, int col0,
-                                               int lane, int M, int N) {
-    chunk_to_cols(v, stg, lane);
-    const int col = col0 + lane;
-    if (col >= N) return;
-    const float b = p.bias[col];
-#pragma unroll 2
-    for (int rr = 0; rr < 32; ++rr) {
-      const int row = row0 + rr;
-      if (row >= M) break;
-      const int bi = row / p.S, s = row - bi * p.S;
-      const float pe = p.pe[static_cast<size_t>(s) * p.d + col];
-      const float frame = stg[rr * 33 + lane] + b + pe;
-      for (int hf = 0; hf < p.halves; ++hf) {
-        const size_t orow = static_cast<size_t>(hf * p.B + bi) * p.S + s;
-        float val = frame;
-        if (s == 0) val = p.tok0[static_cast<size_t>(hf * p.B + bi) * p.d + col] + pe;
-        p.h32[orow * p.d + col] = val;
-        p.h16[orow * p.d + col] = __float2half_rn(val);
-      }
+  static __device__ __forceinline__ void tile_begin(EpiCtx&, const Params&, int, int) {}
+  static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0,
+                                               uint32_t) {
+    const int half = (col0 >> 5) & 1;
+    uint8_t* s32 = ctx.smem + (ctx.seq & 1) * 4096;
+    uint8_t* s16 = ctx.smem + 8192 + ((ctx.seq >> 1) & 1) * 4096;
+    if (ctx.lane == 0) bulk_wait_group_read<1>();  // every group older than the previous chunk's has been read
+    __syncwarp();
+    const int row = row0 + ctx.lane;
+    const int s = (row < ctx.M) ? row % p.S : 0;
+    const float* pb = p.pe_bias + static_cast<size_t>(s) * p.d + col0;
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(pb + 4 * j));
+      float4 o;
+      o.x = __uint_as_float(raw[4 * j + 0]) + a.x;
+      o.y = __uint_as_float(raw[4 * j + 1]) + a.y;
+      o.z = __uint_as_float(raw[4 * j + 2]) + a.z;
+      o.w = __uint_as_float(raw[4 * j + 3]) + a.w;
+      *reinterpret_cast<float4*>(s32 + slab_off(ctx.lane, j)) = o;
+      pk[2 * j] = pack_half2(o.x, o.y);
+      pk[2 * j + 1] = pack_half2(o.z, o.w);
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(s16 + slab_off(ctx.lane, half * 4 + j)) =
+          make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (ctx.lane == 0) {
+      tma_store_2d(&p.h32_c, s32, col0, row0);
+      if (p.halves == 2) tma_store_2d(&p.h32_u, s32, col0, row0);
+      if (half == 1) {
+        tma_store_2d(&p.h16_c, s16, col0 - 32, row0);
+        if (p.halves == 2) tma_store_2d(&p.h16_u, s16, col0 - 32, row0);
+      }
+      bulk_commit_group();
+    }
+    ctx.seq++;
+  }
+  static __device__ __forceinline__ void tile_end(EpiCtx&, const Params&, int, int, uint32_t) {}
+  static __device__ __forceinline__ void finish(EpiCtx& ctx) {
+    if (ctx.lane == 0) bulk_wait_group<0>();
+    __syncwarp();
   }
 };
 
@@ -165,6 +241,8 @@ struct StepState {
 };
 
 struct EpiOutStep {
+  static constexpr int SMEM_PER_WARP = 1024;  // unused
+  static constexpr bool RELEASE_EARLY = true;
   struct Params {
     const float* bias;        // [J]
     const float* x_t;         // [B, J, T]
@@ -179,10 +257,11 @@ struct EpiOutStep {
     int B, S, T, J, mode;
     int clip_denoised;        // clamp x0 to [-1, 1] after the inpainting blend (gaussian_diffusion.py:348-352)
   };
-  static __device__ __forceinline__ void apply(const Params& p, float (&v)[32], float* stg, int row0, int col0,
-                                               int lane, int M, int N) {
-    const int row = row0 + lane;
-    if (row >= M) return;
+  static __device__ __forceinline__ void tile_begin(EpiCtx&, const Params&, int, int) {}
+  static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0,
+                                               uint32_t) {
+    const int row = row0 + ctx.lane;
+    if (row >= ctx.M) return;
     const int b = row / p.S, s = row - b * p.S;
     if (s == 0) return;
     const int t = s - 1;
@@ -196,28 +275,40 @@ struct EpiOutStep {
       nz = (p.noise != nullptr ? p.noise : st.noise + static_cast<long long>(st.done) * st.noise_step_stride) +
            static_cast<long long>(b) * p.noise_batch_stride;
     }
+    // x_out may alias x_t (in-place loop): batch every load of the chunk before the first store so that they are
+    // all in flight together (consecutive lanes = consecutive frames => each load/store is one coalesced line)
+    const size_t base = static_cast<size_t>(b) * p.J * p.T + t;
+    float xv[32], nv[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = col0 + j;
+      xv[j] = (p.mode != 0 && col < p.J) ? p.x_t[base + static_cast<size_t>(col) * p.T] : 0.f;
+      nv[j] = (p.mode != 0 && col < p.J) ? nz[static_cast<size_t>(col) * p.T + t] : 0.f;
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int col = col0 + j;
       if (col < p.J) {
-        const size_t idx = (static_cast<size_t>(b) * p.J + col) * p.T + t;
-        float x0 = v[j] + p.bias[col];
+        const size_t idx = base + static_cast<size_t>(col) * p.T;
+        float x0 = __uint_as_float(raw[j]) + __ldg(p.bias + col);
         if (p.inpaint_mask != nullptr && p.inpaint_mask[idx]) x0 = p.inpaint_motion[idx];
         if (p.clip_denoised) x0 = fminf(fmaxf(x0, -1.f), 1.f);
         if (p.pred_xstart != nullptr) p.pred_xstart[idx] = x0;
         float o = x0;
         if (p.mode == 1) {
-          const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, p.x_t[idx]));
-          o = __fadd_rn(mean, __fmul_rn(sg, nz[static_cast<size_t>(col) * p.T + t]));
+          const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xv[j]));
+          o = __fadd_rn(mean, __fmul_rn(sg, nv[j]));
         } else if (p.mode == 2) {
-          const float eh = __fdiv_rn(__fsub_rn(__fmul_rn(sr, p.x_t[idx]), x0), srm1);
+          const float eh = __fdiv_rn(__fsub_rn(__fmul_rn(sr, xv[j]), x0), srm1);
           const float mean = __fadd_rn(__fmul_rn(x0, sq), __fmul_rn(ce, eh));
-          o = __fadd_rn(mean, __fmul_rn(sg, nz[static_cast<size_t>(col) * p.T + t]));
+          o = __fadd_rn(mean, __fmul_rn(sg, nv[j]));
         }
         p.x_out[idx] = o;
       }
     }
   }
+  static __device__ __forceinline__ void tile_end(EpiCtx&, const Params&, int, int, uint32_t) {}
+  static __device__ __forceinline__ void finish(EpiCtx&) {}
 };
 
 }  // namespace b200

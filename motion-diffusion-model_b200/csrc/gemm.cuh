@@ -2,13 +2,16 @@
 //
 //   warp 0      : TMA producer  (cp.async.bulk.tensor 2-D, 128B-swizzled tiles, STAGES-deep mbarrier ring)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, kind::f16)
-//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue functor -> global)
+//   warps 2..5  : epilogue.  Warp w owns TMEM lanes [32*(w%4), +32) = 32 accumulator rows; thread = row.  Each
+//                 32-column chunk is pulled with tcgen05.ld 32x32b and handed to the fused epilogue functor, which
+//                 stages its 128-byte-per-row output slab in warp-private shared memory (128B swizzle) and ships it
+//                 with a TMA store (and, for the residual variants, brings the residual in with a TMA load).
 //
 // Two TMEM accumulator stages (2 x BLOCK_N fp32 columns) let the epilogue of tile i overlap the MMAs of tile
 // i+1.  Tiles are statically strided over the persistent grid (tile = blockIdx.x + k * gridDim.x, N fastest so
 // concurrently running CTAs share the same A rows in L2).  A is [M,K] row-major (K contiguous), W is the
 // torch nn.Linear layout [N,K] row-major -- both "K-major" UMMA operands, no transposes anywhere.
-// K tails / M tails / N tails rely on TMA out-of-bounds zero fill; the epilogue guards rows and columns.
+// K tails / M tails / N tails rely on TMA out-of-bounds zero fill (loads) and clipping (stores).
 #pragma once
 #include "ptx.cuh"
 
@@ -18,31 +21,46 @@ constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;  // 64 fp16 = 128 B = one swizzle row
 constexpr int GEMM_THREADS = 192;
 constexpr int GEMM_EPI_WARPS = 4;
-constexpr int GEMM_STG_FLOATS = 32 * 33;  // per-warp transpose scratch
+constexpr int GEMM_BAR_BYTES = 512;
 
-template <int BLOCK_N>
+template <int BLOCK_N, class Epi>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;  // 16 KB
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STG_BYTES = GEMM_EPI_WARPS * GEMM_STG_FLOATS * 4;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int budget = 227 * 1024 - 1024 /*alignment slack*/ - STG_BYTES - BAR_BYTES;
+  static constexpr int EPI_BYTES = GEMM_EPI_WARPS * Epi::SMEM_PER_WARP;  // SMEM_PER_WARP is a multiple of 1024
+  static constexpr int budget = 227 * 1024 - 1024 /*alignment slack*/ - EPI_BYTES - GEMM_BAR_BYTES;
   static constexpr int STAGES = (budget / STAGE_BYTES) > 6 ? 6 : (budget / STAGE_BYTES);
-  static constexpr int TOTAL = 1024 + STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES;
+  static constexpr int TOTAL = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + GEMM_BAR_BYTES;
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
+  static_assert(Epi::SMEM_PER_WARP % 1024 == 0, "epilogue slabs must keep 1024-byte alignment (128B swizzle)");
 };
 
 constexpr uint32_t tmem_cols_pow2(int n) { return n <= 32 ? 32u : n <= 64 ? 64u : n <= 128 ? 128u : n <= 256 ? 256u : 512u; }
 
-// Epi must provide:  struct Params;  and
-//   static __device__ void apply(const Params&, float (&v)[32], float* stg, int row0, int col0, int lane, int M, int N)
-// where thread `lane` holds accumulator row (row0 + lane), columns [col0, col0 + 32).
+// Per-warp epilogue context handed to the functor (lives in registers for the whole persistent loop).
+struct EpiCtx {
+  uint8_t* smem;        // warp-private slab, Epi::SMEM_PER_WARP bytes, 1024-byte aligned
+  uint64_t* bars;       // 4 warp-private mbarriers
+  const CUtensorMap* map_c;
+  int lane;
+  int M, N;
+  int col_end;          // first column after the tile in flight (col_base + BLOCK_N)
+  uint32_t seq;         // running chunk / block counter (buffer rotation + mbarrier parity), functor-defined
+};
+
+// Epi interface (all static, called by every lane of an epilogue warp, warp-uniform arguments):
+//   SMEM_PER_WARP                                   bytes of warp-private shared memory
+//   tile_begin(ctx, p, row0, col_base)              before waiting for the accumulator (prefetch residuals here)
+//   chunk(ctx, p, v, row0, col0, tmem_chunk_addr)   v[32] = accumulator row (row0+lane), columns [col0, col0+32)
+//   tile_end(ctx, p, row0, col_base)                after the last chunk
+//   finish(ctx)                                     once, before the CTA exits (drain async stores)
 template <int BLOCK_N, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
-                 int K, typename Epi::Params ep) {
-  using SM = GemmSmem<BLOCK_N>;
+gemm_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_c, int M, int N, int K,
+                 const __grid_constant__ typename Epi::Params ep) {
+  using SM = GemmSmem<BLOCK_N, Epi>;
   constexpr int STAGES = SM::STAGES;
   constexpr uint32_t ACC_STRIDE = (BLOCK_N <= 128) ? 128 : 256;      // TMEM columns between the two accumulators
   constexpr uint32_t TMEM_COLS = tmem_cols_pow2(2 * ACC_STRIDE);
@@ -52,13 +70,15 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
-  float* stg_all = reinterpret_cast<float*>(smem + STAGES * SM::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES + SM::STG_BYTES);
+  uint8_t* epi_smem = smem + STAGES * SM::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + SM::EPI_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* acc_full = bars + 2 * STAGES;       // [2]
   uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* epi_bars = bars + 2 * STAGES + 4;   // [GEMM_EPI_WARPS][4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bars + GEMM_EPI_WARPS * 4);
+  static_assert((2 * 6 + 4 + GEMM_EPI_WARPS * 4) * 8 + 8 <= GEMM_BAR_BYTES, "barrier area too small");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -70,6 +90,7 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_c);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -78,6 +99,7 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], GEMM_EPI_WARPS);
     }
+    for (int s = 0; s < GEMM_EPI_WARPS * 4; ++s) mbar_init(&epi_bars[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -141,34 +163,59 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else {
     // ------------------------------------------------------------ epilogue warps (2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* stg = stg_all + (warp - 2) * GEMM_STG_FLOATS;
+    EpiCtx ctx;
+    ctx.smem = epi_smem + (warp - 2) * Epi::SMEM_PER_WARP;
+    ctx.bars = epi_bars + (warp - 2) * 4;
+    ctx.map_c = &map_c;
+    ctx.lane = lane;
+    ctx.M = M;
+    ctx.N = N;
+    ctx.seq = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const int row0 = m_blk * GEMM_BLOCK_M + q * 32;
+      const int col_base = n_blk * BLOCK_N;
+      const bool live = row0 < M;  // warp-uniform: this warp's 32 rows exist
+      ctx.col_end = col_base + BLOCK_N;
+      if (live) Epi::tile_begin(ctx, ep, row0, col_base);
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
-      const int row0 = m_blk * GEMM_BLOCK_M + q * 32;
       const uint32_t taddr = tmem_base + as * ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
+      if (Epi::RELEASE_EARLY) {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t raw[32];
-        tmem_ld_32x32(taddr + c, raw);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (c + 32 >= BLOCK_N) {
-          // last TMEM read of this accumulator is in registers: release it to the MMA warp early
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[as]);
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t raw[32];
+          tmem_ld_32x32(taddr + c, raw);
+          tmem_ld_wait();
+          if (c + 32 >= BLOCK_N) {
+            // last TMEM read of this accumulator is in registers: release it to the MMA warp early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+          }
+          if (live && col_base + c < N) Epi::chunk(ctx, ep, raw, row0, col_base + c, taddr + c);
         }
-        const int col0 = n_blk * BLOCK_N + c;
-        if (row0 < M && col0 < N) Epi::apply(ep, v, stg, row0, col0, lane, M, N);
+      } else {
+        // the functor owns the accumulator (it may write back to TMEM and read it again): release after tile_end
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t raw[32];
+          tmem_ld_32x32(taddr + c, raw);
+          tmem_ld_wait();
+          if (live && col_base + c < N) Epi::chunk(ctx, ep, raw, row0, col_base + c, taddr + c);
+        }
+      }
+      if (live) Epi::tile_end(ctx, ep, row0, col_base, taddr);
+      if (!Epi::RELEASE_EARLY) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
       }
     }
+    Epi::finish(ctx);
   }
 
   tc_fence_before();

@@ -38,17 +38,30 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __half* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// tok0[b', :] = condproj[b', :] + temb_table[t(b'), :]      (reference model/mdm.py:195,218-220)
+// Conditioning-token rows of the sequence (reference model/mdm.py:195,218-220,251-252):
+//   h[b', s=0, :] = (condproj[b', :] + temb_table[t(b'), :]) + pe[0, :]
 //   t(b') = tvec[b' % B] when tvec != nullptr (model called with explicit timesteps), else timestep_map[state->cur]
-__global__ void tok0_kernel(float* __restrict__ tok0, const float* __restrict__ condproj,
-                            const float* __restrict__ temb_table, const int* __restrict__ tvec,
-                            const int* __restrict__ tmap, const StepState* __restrict__ state, int B, int d,
-                            int temb_rows) {
+// Runs right after the embedding GEMM (which leaves placeholder values in these rows).
+__global__ void tok0_rows_kernel(float* __restrict__ h32, __half* __restrict__ h16, const float* __restrict__ condproj,
+                                 const float* __restrict__ temb_table, const float* __restrict__ pe,
+                                 const int* __restrict__ tvec, const int* __restrict__ tmap,
+                                 const StepState* __restrict__ state, int B, int S, int d, int temb_rows) {
   const int bp = blockIdx.x;
   int t = (tvec != nullptr) ? tvec[bp % B] : tmap[state->cur];
   t = min(max(t, 0), temb_rows - 1);
-  for (int c = threadIdx.x; c < d; c += blockDim.x)
-    tok0[static_cast<size_t>(bp) * d + c] = condproj[static_cast<size_t>(bp) * d + c] + temb_table[static_cast<size_t>(t) * d + c];
+  const size_t row = static_cast<size_t>(bp) * S;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const float v = (condproj[static_cast<size_t>(bp) * d + c] + temb_table[static_cast<size_t>(t) * d + c]) + pe[c];
+    h32[row * d + c] = v;
+    h16[row * d + c] = __float2half_rn(v);
+  }
+}
+
+// pe_bias[s, c] = pe[s, c] + bias[c]  (per (B,T) workspace table for the embedding epilogue)
+__global__ void pe_bias_kernel(float* __restrict__ out, const float* __restrict__ pe, const float* __restrict__ bias,
+                               int S, int d) {
+  const int s = blockIdx.x;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) out[static_cast<size_t>(s) * d + c] = bias[c] + pe[static_cast<size_t>(s) * d + c];
 }
 
 __global__ void step_advance_kernel(StepState* state) {

@@ -28,9 +28,9 @@ def _stream():
     (1000, 1024, 512, 256, 1),       # FFN up + exact GELU
     (777, 512, 1024, 256, 0),        # FFN down shape
     (394, 512, 792, 128, 0),         # embed GEMM: K = 3*264 (K tail: 792 = 12*64 + 24), BLOCK_N 128
-    (394, 288, 1536, 96, 0),         # output GEMM: BLOCK_N 96, N = 3 tiles
-    (394, 264, 1536, 96, 0),         # N tail inside the last 96-wide tile
-    (5, 16, 8, 96, 1),               # tiny
+    (394, 288, 1536, 128, 0),        # N tail inside a 128-wide tile, 64-column slab clipped by the TMA store
+    (394, 264, 1536, 128, 0),        # N tail that ends inside a 32-column chunk
+    (5, 16, 8, 128, 1),              # tiny
 ])
 def test_gemm_tcgen05(M, N, K, bn, act):
     L, lib = _lib()
