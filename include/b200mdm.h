@@ -142,9 +142,10 @@ int64_t b200mdm_launch_count(b200mdm_engine* e, int32_t reset);
  * block_n 256 or 128. */
 int b200mdm_test_gemm_f16(const void* a16_dev, const void* w16_dev, const float* bias_dev, void* out16_dev, int32_t M,
                           int32_t N, int32_t K, int32_t act, int32_t block_n, void* stream);
-/* out16[n*S, d] = softmax(q k^T / sqrt(128) + mask) v per (sample, head); qkv16 [n*S, 3d]; kvlen int32 [n] device */
+/* out16[n*S, d] = softmax(q k^T / sqrt(128) + mask) v per (sample, head); qkv16 [n*S, 3d]; kvlen int32 [n] device.
+ * impl 0: tcgen05 kernel (S <= 256, the one the engine uses); impl 1: mma.sync kernel for longer sequences. */
 int b200mdm_test_attention(const void* qkv16_dev, void* out16_dev, const int32_t* kvlen_dev, int32_t n_samples,
-                           int32_t S, int32_t d, void* stream);
+                           int32_t S, int32_t d, int32_t impl, void* stream);
 /* in-place LayerNorm over rows of h32 [M,512] + fp16 copy */
 int b200mdm_test_layernorm(float* h32_dev, void* h16_dev, const float* gamma_dev, const float* beta_dev, int32_t M,
                            void* stream);

@@ -17,6 +17,7 @@
 
 #include "../../include/b200mdm.h"
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "epilogues.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
@@ -77,6 +78,23 @@ static int make_map_t(CUtensorMap* m, const void* ptr, int elem_bytes, uint64_t 
 static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   return make_map_t(m, ptr, 2, rows, cols, ld, box_rows);
 }
+// fp16 tensor viewed [n][rows][cols] (cols contiguous, row pitch ld elements, sample pitch rows*ld); box {64, box_rows, 1}.
+// The middle dimension is bounded per sample, so tiles that run past the last token of a sample are zero-filled
+// (loads) / clipped (stores) instead of touching the next sample.
+static int make_map_3d(CUtensorMap* m, const void* ptr, uint64_t n, uint64_t rows, uint64_t cols, uint64_t ld,
+                       uint32_t box_rows) {
+  TRY(resolve_driver());
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16) return fail(B200MDM_EINVAL, "TMA operand misaligned");
+  cuuint64_t gdim[3] = {cols, rows, n};
+  cuuint64_t gstr[2] = {ld * 2, rows * ld * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200MDM_ECUDA, "cuTensorMapEncodeTiled(3d) failed (%d)", static_cast<int>(r));
+  return B200MDM_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ engine
 struct Tensor32 {
@@ -124,6 +142,7 @@ struct b200mdm_engine {
   StepState* state = nullptr;
   CUtensorMap m_xin, m_h16, m_att, m_ffn, m_g16;      // A operands (loads, box 128 rows)
   CUtensorMap m_qkv_st, m_ffn_st, m_h32_io;            // epilogue slabs (box 32 rows x 128 bytes)
+  CUtensorMap m_att_q, m_att_kv, m_att_o;             // tcgen05 attention: per-sample 3-D views of qkv16 / att16
   CUtensorMap m_h32_c, m_h32_u, m_h16_c, m_h16_u;      // per-CFG-half views of h32 / h16 for the embedding epilogue
   float* pe_bias = nullptr;
   bool cond_set = false;
@@ -168,6 +187,8 @@ static int init_kernel_attrs() {
   TRY((set_gemm_attr<128, EpiEmbed>()));
   TRY((set_gemm_attr<96, EpiOutStep>()));
   CUDA_TRY(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                AttnTcSmem::total(ATC_MAX_KEYS)));
   done = true;
   return B200MDM_OK;
 }
@@ -182,14 +203,35 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
   return B200MDM_OK;
 }
 
-static int launch_attention(const __half* qkv, __half* out, const int* kvlen, int n_samples, int S, int d, int H,
-                            cudaStream_t s) {
+static int launch_attention_mma(const __half* qkv, __half* out, const int* kvlen, int n_samples, int S, int d, int H,
+                                cudaStream_t s) {
   const int S_pad = (S + 15) & ~15;
   const size_t smem = static_cast<size_t>(S_pad) * 512;
   if (smem > 220 * 1024) return fail(B200MDM_ENOTIMPL, "attention: sequence of %d tokens exceeds the resident-KV kernel", S);
   if (d != H * ATT_DH) return fail(B200MDM_ENOTIMPL, "attention: head_dim must be 128");
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(ATT_DH));
   attention_mma_kernel<<<dim3(H, n_samples), ATT_THREADS, smem, s>>>(qkv, out, kvlen, S, d, scale_log2);
+  CUDA_TRY(cudaGetLastError());
+  return B200MDM_OK;
+}
+
+struct AttnMaps {
+  CUtensorMap q, kv, o;
+};
+static int make_attn_maps(AttnMaps* m, const __half* qkv, __half* out, int n_samples, int S, int d) {
+  const int keys = (S + 15) & ~15;
+  TRY(make_map_3d(&m->q, qkv, n_samples, S, 3 * d, 3 * d, 128));
+  TRY(make_map_3d(&m->kv, qkv, n_samples, S, 3 * d, 3 * d, keys));
+  TRY(make_map_3d(&m->o, out, n_samples, S, d, d, 32));
+  return B200MDM_OK;
+}
+// tcgen05 kernel for sequences of up to 256 tokens (every configuration of the reference: 197 / 61 / 60)
+static int launch_attention_tc(const AttnMaps& m, const int* kvlen, int n_samples, int S, int d, int H, cudaStream_t s) {
+  if (d != H * ATC_DH) return fail(B200MDM_ENOTIMPL, "attention: head_dim must be 128");
+  const int keys = (S + 15) & ~15;
+  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(ATC_DH));
+  attention_tc_kernel<<<dim3(H, n_samples), ATC_THREADS, AttnTcSmem::total(keys), s>>>(m.q, m.kv, m.o, kvlen, S, d, keys,
+                                                                                     scale_log2);
   CUDA_TRY(cudaGetLastError());
   return B200MDM_OK;
 }
@@ -464,6 +506,11 @@ static int build_workspace(b200mdm_engine* e, int B, int T, int halves) {
   TRY(make_map_t(&e->m_qkv_st, e->qkv16, 2, M, 3 * d, 3 * d, 32));
   TRY(make_map_t(&e->m_ffn_st, e->ffn16, 2, M, e->ff, e->ff, 32));
   TRY(make_map_t(&e->m_h32_io, e->h32, 4, M, d, d, 32));
+  if (S <= ATC_MAX_KEYS) {
+    AttnMaps am;
+    TRY(make_attn_maps(&am, e->qkv16, e->att16, Bp, S, d));
+    e->m_att_q = am.q; e->m_att_kv = am.kv; e->m_att_o = am.o;
+  }
   TRY(make_map_t(&e->m_h32_c, e->h32, 4, MB, d, d, 32));
   TRY(make_map_t(&e->m_h16_c, e->h16, 2, MB, d, d, 32));
   TRY(make_map_t(&e->m_h32_u, e->h32 + (halves == 2 ? MB * d : 0), 4, MB, d, d, 32));
@@ -579,7 +626,12 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
       EpiBiasF16<false>::Params p{w.bqkv};
       TRY((launch_gemm<256, EpiBiasF16<false>>(e->m_h16, w.m_wqkv, e->m_qkv_st, e->M, 3 * d, d, p, s, e->num_sms)));
     }
-    TRY(launch_attention(e->qkv16, e->att16, e->kvlen, e->Bp, S, d, e->H, s));
+    if (S <= ATC_MAX_KEYS) {
+      AttnMaps am{e->m_att_q, e->m_att_kv, e->m_att_o};
+      TRY(launch_attention_tc(am, e->kvlen, e->Bp, S, d, e->H, s));
+    } else {
+      TRY(launch_attention_mma(e->qkv16, e->att16, e->kvlen, e->Bp, S, d, e->H, s));
+    }
     {
       EpiResidualF32::Params p{w.bo};
       TRY((launch_gemm<256, EpiResidualF32>(e->m_att, w.m_wo, e->m_h32_io, e->M, d, d, p, s, e->num_sms)));
@@ -802,11 +854,18 @@ extern "C" int b200mdm_test_gemm_f16(const void* a16_dev, const void* w16_dev, c
 }
 
 extern "C" int b200mdm_test_attention(const void* qkv16_dev, void* out16_dev, const int32_t* kvlen_dev,
-                                      int32_t n_samples, int32_t S, int32_t d, void* stream) {
+                                      int32_t n_samples, int32_t S, int32_t d, int32_t impl, void* stream) {
   if (!qkv16_dev || !out16_dev || !kvlen_dev || n_samples <= 0 || S <= 0) return fail(B200MDM_EINVAL, "bad argument");
   TRY(init_kernel_attrs());
-  return launch_attention(static_cast<const __half*>(qkv16_dev), static_cast<__half*>(out16_dev), kvlen_dev, n_samples, S,
-                          d, d / ATT_DH, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (impl == 0) {
+    if (S > ATC_MAX_KEYS) return fail(B200MDM_EINVAL, "tcgen05 attention handles at most %d tokens", ATC_MAX_KEYS);
+    AttnMaps am;
+    TRY(make_attn_maps(&am, static_cast<const __half*>(qkv16_dev), static_cast<__half*>(out16_dev), n_samples, S, d));
+    return launch_attention_tc(am, kvlen_dev, n_samples, S, d, d / ATC_DH, s);
+  }
+  return launch_attention_mma(static_cast<const __half*>(qkv16_dev), static_cast<__half*>(out16_dev), kvlen_dev, n_samples,
+                              S, d, d / ATT_DH, s);
 }
 
 extern "C" int b200mdm_test_layernorm(float* h32_dev, void* h16_dev, const float* gamma_dev, const float* beta_dev,

@@ -274,3 +274,12 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 
 }  // namespace b200
+
+namespace b200 {
+// 3-D tiled store, shared -> global (bulk async-group completion); out-of-bounds rows / columns are dropped.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+}  // namespace b200

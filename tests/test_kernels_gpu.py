@@ -49,16 +49,17 @@ def test_gemm_tcgen05(M, N, K, bn, act):
     assert err < 4e-3 * max(1.0, ref.abs().max().item()), err
 
 
+@pytest.mark.parametrize("impl", [0, 1])
 @pytest.mark.parametrize("n,S,kv", [(3, 197, [197, 121, 58]), (2, 41, [41, 1]), (4, 61, [61, 46, 31, 2]), (1, 16, [16]),
-                                    (2, 33, [20, 33])])
-def test_attention(n, S, kv):
+                                    (2, 33, [20, 33]), (2, 256, [256, 130]), (2, 129, [129, 128])])
+def test_attention(n, S, kv, impl):
     L, lib = _lib()
     d, H, dh = 512, 4, 128
     g = torch.Generator(device="cuda").manual_seed(S)
     qkv = torch.randn(n * S, 3 * d, device="cuda", generator=g).half()
     kvlen = torch.tensor(kv, device="cuda", dtype=torch.int32)
     out = torch.full((n * S, d), float("nan"), device="cuda", dtype=torch.float16)
-    L.check(lib.b200mdm_test_attention(_p(qkv), _p(out), _p(kvlen), n, S, d, _stream()))
+    L.check(lib.b200mdm_test_attention(_p(qkv), _p(out), _p(kvlen), n, S, d, impl, _stream()))
     torch.cuda.synchronize()
     q, k, v = qkv.float().view(n, S, 3, H, dh).permute(2, 0, 3, 1, 4)
     s = q @ k.transpose(-1, -2) / dh ** 0.5
