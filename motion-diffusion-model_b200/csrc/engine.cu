@@ -20,6 +20,7 @@
 #include "attention_tc.cuh"
 #include "epilogues.cuh"
 #include "gemm.cuh"
+#include "gemm2.cuh"
 #include "kernels.cuh"
 
 using namespace b200;
@@ -106,7 +107,7 @@ struct Tensor32 {
 struct LayerW {
   __half *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
   const float *bqkv, *bo, *b1, *b2, *g1, *be1, *g2, *be2;
-  CUtensorMap m_wqkv, m_wo, m_w1, m_w2;
+  CUtensorMap m_wqkv, m_wo, m_w1, m_w2;   // box 128 rows: each CTA of a pair stages half of a 256-row W tile
 };
 
 struct GraphKey {
@@ -176,6 +177,11 @@ static int set_gemm_attr() {
                                 GemmSmem<BN, Epi>::TOTAL));
   return B200MDM_OK;
 }
+template <class Epi>
+static int set_gemm2_attr() {
+  CUDA_TRY(cudaFuncSetAttribute(gemm2_f16_tcgen05<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<Epi>::TOTAL));
+  return B200MDM_OK;
+}
 static int init_kernel_attrs() {
   static bool done = false;
   if (done) return B200MDM_OK;
@@ -184,6 +190,9 @@ static int init_kernel_attrs() {
   TRY((set_gemm_attr<128, EpiBiasF16<false>>()));
   TRY((set_gemm_attr<128, EpiBiasF16<true>>()));
   TRY((set_gemm_attr<256, EpiResidualF32>()));
+  TRY((set_gemm2_attr<EpiBiasF16<false>>()));
+  TRY((set_gemm2_attr<EpiBiasF16<true>>()));
+  TRY((set_gemm2_attr<EpiResidualF32>()));
   TRY((set_gemm_attr<128, EpiEmbed>()));
   TRY((set_gemm_attr<96, EpiOutStep>()));
   CUDA_TRY(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -199,6 +208,18 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
   const int tiles = ((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
   gemm_f16_tcgen05<BN, Epi><<<grid, GEMM_THREADS, GemmSmem<BN, Epi>::TOTAL, s>>>(a, b, c, M, N, K, p);
+  CUDA_TRY(cudaGetLastError());
+  return B200MDM_OK;
+}
+
+// CTA-pair GEMM (256 x 256 tiles): a = A map (box 128 rows), b = W map with box 128 rows (half tile per CTA)
+template <class Epi>
+static int launch_gemm2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int M, int N, int K,
+                        const typename Epi::Params& p, cudaStream_t s, int num_sms) {
+  const int tiles = ((M + GEMM2_TILE_M - 1) / GEMM2_TILE_M) * ((N + GEMM2_BLOCK_N - 1) / GEMM2_BLOCK_N);
+  const int max_clusters = num_sms / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  gemm2_f16_tcgen05<Epi><<<2 * clusters, GEMM_THREADS, Gemm2Smem<Epi>::TOTAL, s>>>(a, b, c, M, N, K, p);
   CUDA_TRY(cudaGetLastError());
   return B200MDM_OK;
 }
@@ -434,10 +455,10 @@ extern "C" int b200mdm_finalize_weights(b200mdm_engine* e, void* stream) {
     TRY(to_f16(wo, &w.wo, static_cast<size_t>(d) * d, s));
     TRY(to_f16(w1, &w.w1, static_cast<size_t>(ff) * d, s));
     TRY(to_f16(w2, &w.w2, static_cast<size_t>(d) * ff, s));
-    TRY(make_map(&w.m_wqkv, w.wqkv, 3 * d, d, d, 256));
-    TRY(make_map(&w.m_wo, w.wo, d, d, d, 256));
-    TRY(make_map(&w.m_w1, w.w1, ff, d, d, 256));
-    TRY(make_map(&w.m_w2, w.w2, d, ff, ff, 256));
+    TRY(make_map(&w.m_wqkv, w.wqkv, 3 * d, d, d, 128));
+    TRY(make_map(&w.m_wo, w.wo, d, d, d, 128));
+    TRY(make_map(&w.m_w1, w.w1, ff, d, d, 128));
+    TRY(make_map(&w.m_w2, w.w2, d, ff, ff, 128));
   }
   // timestep-embedding MLP for every model timestep: temb[t] = W2 silu(W1 pe[t] + b1) + b2
   const int R = e->cfg.temb_rows;
@@ -624,7 +645,7 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
     const LayerW& w = e->layers[l];
     {
       EpiBiasF16<false>::Params p{w.bqkv};
-      TRY((launch_gemm<256, EpiBiasF16<false>>(e->m_h16, w.m_wqkv, e->m_qkv_st, e->M, 3 * d, d, p, s, e->num_sms)));
+      TRY((launch_gemm2<EpiBiasF16<false>>(e->m_h16, w.m_wqkv, e->m_qkv_st, e->M, 3 * d, d, p, s, e->num_sms)));
     }
     if (S <= ATC_MAX_KEYS) {
       AttnMaps am{e->m_att_q, e->m_att_kv, e->m_att_o};
@@ -634,16 +655,16 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
     }
     {
       EpiResidualF32::Params p{w.bo};
-      TRY((launch_gemm<256, EpiResidualF32>(e->m_att, w.m_wo, e->m_h32_io, e->M, d, d, p, s, e->num_sms)));
+      TRY((launch_gemm2<EpiResidualF32>(e->m_att, w.m_wo, e->m_h32_io, e->M, d, d, p, s, e->num_sms)));
     }
     TRY(launch_layernorm(e->h32, e->h16, w.g1, w.be1, e->M, s));
     {
       EpiBiasF16<true>::Params p{w.b1};
-      TRY((launch_gemm<256, EpiBiasF16<true>>(e->m_h16, w.m_w1, e->m_ffn_st, e->M, ff, d, p, s, e->num_sms)));
+      TRY((launch_gemm2<EpiBiasF16<true>>(e->m_h16, w.m_w1, e->m_ffn_st, e->M, ff, d, p, s, e->num_sms)));
     }
     {
       EpiResidualF32::Params p{w.b2};
-      TRY((launch_gemm<256, EpiResidualF32>(e->m_ffn, w.m_w2, e->m_h32_io, e->M, d, ff, p, s, e->num_sms)));
+      TRY((launch_gemm2<EpiResidualF32>(e->m_ffn, w.m_w2, e->m_h32_io, e->M, d, ff, p, s, e->num_sms)));
     }
     TRY(launch_layernorm(e->h32, e->h16, w.g2, w.be2, e->M, s));
     nk += 7;
@@ -846,10 +867,22 @@ extern "C" int b200mdm_test_gemm_f16(const void* a16_dev, const void* w16_dev, c
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (block_n == 512) {  // CTA-pair kernel, 256 x 256 pair tiles
+    CUtensorMap ma, mb, mc;
+    TRY(make_map(&ma, a16_dev, M, K, K, GEMM_BLOCK_M));
+    TRY(make_map(&mb, w16_dev, N, K, K, 128));
+    TRY(make_map_t(&mc, out16_dev, 2, M, N, N, 32));
+    if (act) {
+      EpiBiasF16<true>::Params p{bias_dev};
+      return launch_gemm2<EpiBiasF16<true>>(ma, mb, mc, M, N, K, p, s, sms);
+    }
+    EpiBiasF16<false>::Params p{bias_dev};
+    return launch_gemm2<EpiBiasF16<false>>(ma, mb, mc, M, N, K, p, s, sms);
+  }
   switch (block_n) {
     case 256: return test_gemm_bn<256>(a16_dev, w16_dev, bias_dev, out16_dev, M, N, K, act, s, sms);
     case 128: return test_gemm_bn<128>(a16_dev, w16_dev, bias_dev, out16_dev, M, N, K, act, s, sms);
-    default: return fail(B200MDM_EINVAL, "block_n must be 256 or 128");
+    default: return fail(B200MDM_EINVAL, "block_n must be 512 (CTA pair), 256 or 128");
   }
 }
 

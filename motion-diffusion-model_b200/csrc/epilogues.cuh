@@ -36,6 +36,27 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return x * phi;
 }
 
+// Stage the bias of the tile in flight (up to 256 columns) in warp-private shared memory so that the row-owning
+// threads read it with broadcast LDS instead of dependent global loads inside the chunk loop.
+__device__ __forceinline__ void stage_bias(float* bs, const float* bias, int col_base, int N, int lane) {
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int idx = i * 128 + lane * 4;
+    const int col = col_base + idx;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col + 3 < N) {
+      v = __ldg(reinterpret_cast<const float4*>(bias + col));
+    } else {
+      if (col + 0 < N) v.x = bias[col + 0];
+      if (col + 1 < N) v.y = bias[col + 1];
+      if (col + 2 < N) v.z = bias[col + 2];
+    }
+    *reinterpret_cast<float4*>(bs + idx) = v;
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -47,12 +68,14 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // box {64 cols, 32 rows}, SWIZZLE_128B.
 template <bool GELU>
 struct EpiBiasF16 {
-  static constexpr int SMEM_PER_WARP = 2 * 4096;
+  static constexpr int SMEM_PER_WARP = 2 * 4096 + 1024;  // two output slabs + the tile's bias
   static constexpr bool RELEASE_EARLY = true;
   struct Params {
     const float* bias;
   };
-  static __device__ __forceinline__ void tile_begin(EpiCtx&, const Params&, int, int) {}
+  static __device__ __forceinline__ void tile_begin(EpiCtx& ctx, const Params& p, int, int col_base) {
+    stage_bias(reinterpret_cast<float*>(ctx.smem + 8192), p.bias, col_base, ctx.N, ctx.lane);
+  }
   static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0,
                                                uint32_t) {
     const int half = (col0 >> 5) & 1;
@@ -62,17 +85,11 @@ struct EpiBiasF16 {
       if (ctx.lane == 0) bulk_wait_group_read<1>();
       __syncwarp();
     }
+    const float* bs = reinterpret_cast<const float*>(ctx.smem + 8192) + (col0 - ctx.col_base);
     uint32_t pk[16];
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col0 + j + 3 < ctx.N) {
-        b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-      } else {
-        if (col0 + j + 0 < ctx.N) b.x = p.bias[col0 + j + 0];
-        if (col0 + j + 1 < ctx.N) b.y = p.bias[col0 + j + 1];
-        if (col0 + j + 2 < ctx.N) b.z = p.bias[col0 + j + 2];
-      }
+      const float4 b = *reinterpret_cast<const float4*>(bs + j);
       float x0 = __uint_as_float(raw[j + 0]) + b.x, x1 = __uint_as_float(raw[j + 1]) + b.y;
       float x2 = __uint_as_float(raw[j + 2]) + b.z, x3 = __uint_as_float(raw[j + 3]) + b.w;
       if (GELU) {
@@ -108,7 +125,7 @@ struct EpiBiasF16 {
 // registers, write back into the same slab, TMA store.  map_c: fp32 [M, N], box {32 cols, 32 rows}, SWIZZLE_128B.
 struct EpiResidualF32 {
   static constexpr int NBUF = 3;
-  static constexpr int SMEM_PER_WARP = NBUF * 4096;
+  static constexpr int SMEM_PER_WARP = NBUF * 4096 + 1024;  // three residual/output slabs + the tile's bias
   static constexpr bool RELEASE_EARLY = true;
   struct Params {
     const float* bias;
@@ -122,20 +139,22 @@ struct EpiResidualF32 {
       tma_load_2d(ctx.smem + b * 4096, ctx.map_c, &ctx.bars[b], col0, row0);
     }
   }
-  static __device__ __forceinline__ void tile_begin(EpiCtx& ctx, const Params&, int row0, int col_base) {
+  static __device__ __forceinline__ void tile_begin(EpiCtx& ctx, const Params& p, int row0, int col_base) {
     prefetch(ctx, ctx.seq, row0, col_base);
+    stage_bias(reinterpret_cast<float*>(ctx.smem + NBUF * 4096), p.bias, col_base, ctx.N, ctx.lane);
   }
   static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0,
                                                uint32_t) {
     const uint32_t b = ctx.seq % NBUF;
     if (col0 + 32 < ctx.col_end && col0 + 32 < ctx.N) prefetch(ctx, ctx.seq + 1, row0, col0 + 32);
     uint8_t* slab = ctx.smem + b * 4096;
+    const float* bs = reinterpret_cast<const float*>(ctx.smem + NBUF * 4096) + (col0 - ctx.col_base);
     mbar_wait(&ctx.bars[b], (ctx.seq / NBUF) & 1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float4* cell = reinterpret_cast<float4*>(slab + slab_off(ctx.lane, j));
       const float4 r = *cell;
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
+      const float4 bb = *reinterpret_cast<const float4*>(bs + 4 * j);
       float4 o;
       o.x = r.x + (__uint_as_float(raw[4 * j + 0]) + bb.x);
       o.y = r.y + (__uint_as_float(raw[4 * j + 1]) + bb.y);

@@ -45,6 +45,7 @@ struct EpiCtx {
   const CUtensorMap* map_c;
   int lane;
   int M, N;
+  int col_base;         // first column of the tile in flight
   int col_end;          // first column after the tile in flight (col_base + BLOCK_N)
   uint32_t seq;         // running chunk / block counter (buffer rotation + mbarrier parity), functor-defined
 };
@@ -179,6 +180,7 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int row0 = m_blk * GEMM_BLOCK_M + q * 32;
       const int col_base = n_blk * BLOCK_N;
       const bool live = row0 < M;  // warp-uniform: this warp's 32 rows exist
+      ctx.col_base = col_base;
       ctx.col_end = col_base + BLOCK_N;
       if (live) Epi::tile_begin(ctx, ep, row0, col_base);
       mbar_wait(&acc_full[as], aphase);

@@ -31,6 +31,12 @@ def _stream():
     (394, 288, 1536, 128, 0),        # N tail inside a 128-wide tile, 64-column slab clipped by the TMA store
     (394, 264, 1536, 128, 0),        # N tail that ends inside a 32-column chunk
     (5, 16, 8, 128, 1),              # tiny
+    (256, 256, 64, 512, 0),          # CTA-pair kernel: one 256x256 tile, one k-block
+    (700, 512, 512, 512, 0),         # pair: M tail inside the second CTA (700 = 2*256 + 188), pipeline wraps
+    (25216 // 8, 1536, 512, 512, 0), # pair: QKV shape
+    (3000, 1024, 512, 512, 1),       # pair: FFN up + GELU
+    (130, 512, 1024, 512, 0),        # pair: second CTA holds 2 live rows only
+    (100, 264, 512, 512, 0),         # pair: second CTA entirely out of range, N tail
 ])
 def test_gemm_tcgen05(M, N, K, bn, act):
     L, lib = _lib()
