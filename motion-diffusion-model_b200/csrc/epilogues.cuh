@@ -77,7 +77,7 @@ struct EpiBiasF16 {
     stage_bias(reinterpret_cast<float*>(ctx.smem + 8192), p.bias, col_base, ctx.N, ctx.lane);
   }
   static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0,
-                                               uint32_t) {
+                                               int) {
     const int half = (col0 >> 5) & 1;
     uint8_t* slab = ctx.smem + (ctx.seq & 1) * 4096;
     if (half == 0) {
@@ -124,29 +124,33 @@ struct EpiBiasF16 {
 // Per 32-column chunk: TMA load of the residual slab (issued one chunk ahead, three rotating buffers), add in
 // registers, write back into the same slab, TMA store.  map_c: fp32 [M, N], box {32 cols, 32 rows}, SWIZZLE_128B.
 struct EpiResidualF32 {
-  static constexpr int NBUF = 3;
-  static constexpr int SMEM_PER_WARP = NBUF * 4096 + 1024;  // three residual/output slabs + the tile's bias
+  static constexpr int NBUF = 2;
+  static constexpr int SMEM_PER_WARP = NBUF * 4096 + 1024;  // two residual/output slabs + the tile's bias
   static constexpr bool RELEASE_EARLY = true;
   struct Params {
     const float* bias;
   };
   static __device__ __forceinline__ void prefetch(EpiCtx& ctx, uint32_t seq, int row0, int col0) {
-    // buffer seq % NBUF was last stored from NBUF chunks ago; only the most recent store may stay in flight
+    // buffer seq % NBUF was last stored from NBUF chunks ago: with two buffers that is the most recent store
     if (ctx.lane == 0) {
-      bulk_wait_group_read<1>();
+      bulk_wait_group_read<0>();
       const uint32_t b = seq % NBUF;
       mbar_expect_tx(&ctx.bars[b], 4096);
       tma_load_2d(ctx.smem + b * 4096, ctx.map_c, &ctx.bars[b], col0, row0);
     }
   }
   static __device__ __forceinline__ void tile_begin(EpiCtx& ctx, const Params& p, int row0, int col_base) {
-    prefetch(ctx, ctx.seq, row0, col_base);
+    // NOTE: tile_begin does not know which column block this warp starts with; chunk() of the first chunk issues it
     stage_bias(reinterpret_cast<float*>(ctx.smem + NBUF * 4096), p.bias, col_base, ctx.N, ctx.lane);
   }
   static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0,
-                                               uint32_t) {
+                                               int next_col0) {
     const uint32_t b = ctx.seq % NBUF;
-    if (col0 + 32 < ctx.col_end && col0 + 32 < ctx.N) prefetch(ctx, ctx.seq + 1, row0, col0 + 32);
+    if (!ctx.primed) {  // first chunk of this warp in the tile: nothing was prefetched yet
+      prefetch(ctx, ctx.seq, row0, col0);
+      ctx.primed = true;
+    }
+    if (next_col0 >= 0) prefetch(ctx, ctx.seq + 1, row0, next_col0); else ctx.primed = false;
     uint8_t* slab = ctx.smem + b * 4096;
     const float* bs = reinterpret_cast<const float*>(ctx.smem + NBUF * 4096) + (col0 - ctx.col_base);
     mbar_wait(&ctx.bars[b], (ctx.seq / NBUF) & 1);
@@ -194,7 +198,7 @@ struct EpiEmbed {
   };
   static __device__ __forceinline__ void tile_begin(EpiCtx&, const Params&, int, int) {}
   static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0,
-                                               uint32_t) {
+                                               int) {
     const int half = (col0 >> 5) & 1;
     uint8_t* s32 = ctx.smem + (ctx.seq & 1) * 4096;
     uint8_t* s16 = ctx.smem + 8192 + ((ctx.seq >> 1) & 1) * 4096;
@@ -278,7 +282,7 @@ struct EpiOutStep {
   };
   static __device__ __forceinline__ void tile_begin(EpiCtx&, const Params&, int, int) {}
   static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0,
-                                               uint32_t) {
+                                               int) {
     const int row = row0 + ctx.lane;
     if (row >= ctx.M) return;
     const int b = row / p.S, s = row - b * p.S;

@@ -2,8 +2,9 @@
 //
 //   warp 0      : TMA producer  (cp.async.bulk.tensor 2-D, 128B-swizzled tiles, STAGES-deep mbarrier ring)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, kind::f16)
-//   warps 2..5  : epilogue.  Warp w owns TMEM lanes [32*(w%4), +32) = 32 accumulator rows; thread = row.  Each
-//                 32-column chunk is pulled with tcgen05.ld 32x32b and handed to the fused epilogue functor, which
+//   warps 2..9  : epilogue.  Warp w owns TMEM lanes [32*(w%4), +32) = 32 accumulator rows (thread = row) and every
+//                 other 64-column block of the tile (two warps share a lane quarter).  Each 32-column chunk is pulled
+//                 with tcgen05.ld 32x32b (double-buffered in registers) and handed to the fused epilogue functor, which
 //                 stages its 128-byte-per-row output slab in warp-private shared memory (128B swizzle) and ships it
 //                 with a TMA store (and, for the residual variants, brings the residual in with a TMA load).
 //
@@ -19,8 +20,8 @@ namespace b200 {
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;  // 64 fp16 = 128 B = one swizzle row
-constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_EPI_WARPS = 4;
+constexpr int GEMM_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each owning every other 64-column block
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_BAR_BYTES = 512;
 
 template <int BLOCK_N, class Epi>
@@ -48,12 +49,64 @@ struct EpiCtx {
   int col_base;         // first column of the tile in flight
   int col_end;          // first column after the tile in flight (col_base + BLOCK_N)
   uint32_t seq;         // running chunk / block counter (buffer rotation + mbarrier parity), functor-defined
+  bool primed;          // functor-defined: a prefetch for the chunk about to be processed is already in flight
 };
+
+// One tile's epilogue for one warp: chunks c = 64*part, 64*part+32, 64*part+128, ... of the BLOCK_N accumulator
+// columns.  tcgen05.ld of the next chunk is issued before the current chunk is processed (register double buffer);
+// `release` (accumulator free) runs as soon as this warp's last TMEM read has landed.
+template <int BLOCK_N>
+__device__ __forceinline__ int epi_next_chunk(int c) {
+  return ((c & 32) == 0 && c + 32 < BLOCK_N) ? c + 32 : (c & ~63) + 128;
+}
+template <int BLOCK_N, class Epi, class Release>
+__device__ __forceinline__ void epilogue_tile(EpiCtx& ctx, const typename Epi::Params& ep, uint32_t taddr, int row0,
+                                              int col_base, int part, uint64_t* acc_full_bar, uint32_t acc_phase,
+                                              Release release) {
+  const bool live = row0 < ctx.M;  // warp-uniform: this warp's 32 rows exist
+  ctx.col_base = col_base;
+  ctx.col_end = col_base + BLOCK_N;
+  if (live) Epi::tile_begin(ctx, ep, row0, col_base);
+  mbar_wait(acc_full_bar, acc_phase);
+  tc_fence_after();
+  auto done_reading = [&]() {
+    tc_fence_before();
+    __syncwarp();
+    if (ctx.lane == 0) release();
+  };
+  auto run = [&](uint32_t (&raw)[32], int c, int cn) {
+    if (live && col_base + c < ctx.N)
+      Epi::chunk(ctx, ep, raw, row0, col_base + c, (cn < BLOCK_N && col_base + cn < ctx.N) ? col_base + cn : -1);
+  };
+  uint32_t raw_a[32], raw_b[32];
+  int c = part * 64;
+  if (c >= BLOCK_N) {
+    done_reading();
+  } else {
+    tmem_ld_32x32(taddr + c, raw_a);
+#pragma unroll 1
+    while (true) {
+      const int cn = epi_next_chunk<BLOCK_N>(c);
+      tmem_ld_wait();
+      if (cn < BLOCK_N) tmem_ld_32x32(taddr + cn, raw_b); else done_reading();
+      run(raw_a, c, cn);
+      if (cn >= BLOCK_N) break;
+      const int cnn = epi_next_chunk<BLOCK_N>(cn);
+      tmem_ld_wait();
+      if (cnn < BLOCK_N) tmem_ld_32x32(taddr + cnn, raw_a); else done_reading();
+      run(raw_b, cn, cnn);
+      if (cnn >= BLOCK_N) break;
+      c = cnn;
+    }
+  }
+  if (live) Epi::tile_end(ctx, ep, row0, col_base, taddr);
+}
 
 // Epi interface (all static, called by every lane of an epilogue warp, warp-uniform arguments):
 //   SMEM_PER_WARP                                   bytes of warp-private shared memory
 //   tile_begin(ctx, p, row0, col_base)              before waiting for the accumulator (prefetch residuals here)
-//   chunk(ctx, p, v, row0, col0, tmem_chunk_addr)   v[32] = accumulator row (row0+lane), columns [col0, col0+32)
+//   chunk(ctx, p, v, row0, col0, next_col0)         v[32] = accumulator row (row0+lane), columns [col0, col0+32);
+//                                                   next_col0 = first column of this warp's next chunk in the tile, or -1
 //   tile_end(ctx, p, row0, col_base)                after the last chunk
 //   finish(ctx)                                     once, before the CTA exits (drain async stores)
 template <int BLOCK_N, class Epi>
@@ -162,8 +215,9 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps (2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------ epilogue warps (2..9)
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int part = (warp - 2) >> 2;  // which 64-column blocks of the tile this warp owns
     EpiCtx ctx;
     ctx.smem = epi_smem + (warp - 2) * Epi::SMEM_PER_WARP;
     ctx.bars = epi_bars + (warp - 2) * 4;
@@ -172,50 +226,16 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     ctx.M = M;
     ctx.N = N;
     ctx.seq = 0;
+    ctx.primed = false;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int row0 = m_blk * GEMM_BLOCK_M + q * 32;
-      const int col_base = n_blk * BLOCK_N;
-      const bool live = row0 < M;  // warp-uniform: this warp's 32 rows exist
-      ctx.col_base = col_base;
-      ctx.col_end = col_base + BLOCK_N;
-      if (live) Epi::tile_begin(ctx, ep, row0, col_base);
-      mbar_wait(&acc_full[as], aphase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + as * ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
-      if (Epi::RELEASE_EARLY) {
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
-          uint32_t raw[32];
-          tmem_ld_32x32(taddr + c, raw);
-          tmem_ld_wait();
-          if (c + 32 >= BLOCK_N) {
-            // last TMEM read of this accumulator is in registers: release it to the MMA warp early
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[as]);
-          }
-          if (live && col_base + c < N) Epi::chunk(ctx, ep, raw, row0, col_base + c, taddr + c);
-        }
-      } else {
-        // the functor owns the accumulator (it may write back to TMEM and read it again): release after tile_end
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
-          uint32_t raw[32];
-          tmem_ld_32x32(taddr + c, raw);
-          tmem_ld_wait();
-          if (live && col_base + c < N) Epi::chunk(ctx, ep, raw, row0, col_base + c, taddr + c);
-        }
-      }
-      if (live) Epi::tile_end(ctx, ep, row0, col_base, taddr);
-      if (!Epi::RELEASE_EARLY) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[as]);
-      }
+      epilogue_tile<BLOCK_N, Epi>(ctx, ep, taddr, row0, n_blk * BLOCK_N, part, &acc_full[as], aphase,
+                                  [&]() { mbar_arrive(&acc_empty[as]); });
     }
     Epi::finish(ctx);
   }

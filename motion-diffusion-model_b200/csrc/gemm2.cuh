@@ -11,7 +11,7 @@
 //                CTAs are reported to the LEADER's "full" barrier.
 //   warp 1     : TMEM allocator (pair-wide allocation); in the leader also the single-thread MMA issuer.  tcgen05.commit
 //                multicasts "slot free" / "accumulator ready" to the barriers of both CTAs.
-//   warps 2..5 : epilogue of this CTA's 128 accumulator rows (same functors as gemm.cuh); accumulator release is
+//   warps 2..9 : epilogue of this CTA's 128 accumulator rows (same functors as gemm.cuh); accumulator release is
 //                reported to the leader's barrier (remote mbarrier arrive).
 #pragma once
 #include "gemm.cuh"
@@ -144,8 +144,9 @@ gemm2_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps (2..5), both CTAs
+    // ------------------------------------------------------------ epilogue warps (2..9), both CTAs
     const int q = warp & 3;
+    const int part = (warp - 2) >> 2;
     EpiCtx ctx;
     ctx.smem = epi_smem + (warp - 2) * Epi::SMEM_PER_WARP;
     ctx.bars = epi_bars + (warp - 2) * 4;
@@ -154,36 +155,18 @@ gemm2_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     ctx.M = M;
     ctx.N = N;
     ctx.seq = 0;
+    ctx.primed = false;
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int row0 = m_blk * GEMM2_TILE_M + static_cast<int>(rank) * 128 + q * 32;
-      const int col_base = n_blk * GEMM2_BLOCK_N;
-      const bool live = row0 < M;
-      ctx.col_base = col_base;
-      ctx.col_end = col_base + GEMM2_BLOCK_N;
-      if (live) Epi::tile_begin(ctx, ep, row0, col_base);
-      mbar_wait(&acc_full[as], aphase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + as * ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < GEMM2_BLOCK_N; c += 32) {
-        uint32_t raw[32];
-        tmem_ld_32x32(taddr + c, raw);
-        tmem_ld_wait();
-        if (c + 32 >= GEMM2_BLOCK_N) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (leader) mbar_arrive(&acc_empty[as]);
-            else mbar_arrive_remote(mapa_shared(smem_u32(&acc_empty[as]), 0));
-          }
-        }
-        if (live && col_base + c < N) Epi::chunk(ctx, ep, raw, row0, col_base + c, taddr + c);
-      }
-      if (live) Epi::tile_end(ctx, ep, row0, col_base, taddr);
+      epilogue_tile<GEMM2_BLOCK_N, Epi>(ctx, ep, taddr, row0, n_blk * GEMM2_BLOCK_N, part, &acc_full[as], aphase, [&]() {
+        if (leader) mbar_arrive(&acc_empty[as]);
+        else mbar_arrive_remote(mapa_shared(smem_u32(&acc_empty[as]), 0));
+      });
     }
     Epi::finish(ctx);
   }
