@@ -19,7 +19,7 @@ SYMBOLS = [
     "b200mdm_last_error", "b200mdm_version", "b200mdm_create", "b200mdm_destroy", "b200mdm_load_weight",
     "b200mdm_finalize_weights", "b200mdm_set_schedule", "b200mdm_set_cond", "b200mdm_set_inpaint",
     "b200mdm_denoise", "b200mdm_sample_step", "b200mdm_sample_loop", "b200mdm_q_sample", "b200mdm_launch_count",
-    "b200mdm_test_gemm_f16", "b200mdm_test_attention", "b200mdm_test_layernorm",
+    "b200mdm_test_gemm_f16", "b200mdm_test_attention", "b200mdm_test_gemm_resid_ln", "b200mdm_test_layernorm",
 ]
 
 
@@ -68,6 +68,7 @@ def load():
     lib.b200mdm_launch_count.restype = i64
     lib.b200mdm_test_gemm_f16.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.b200mdm_test_attention.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.b200mdm_test_gemm_resid_ln.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.b200mdm_test_layernorm.argtypes = [vp, vp, vp, vp, i32, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)

@@ -21,6 +21,8 @@
 #include "epilogues.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
+#include "gemm2_ln.cuh"
+#include "gemm_ln.cuh"
 #include "kernels.cuh"
 
 using namespace b200;
@@ -108,6 +110,7 @@ struct LayerW {
   __half *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
   const float *bqkv, *bo, *b1, *b2, *g1, *be1, *g2, *be2;
   CUtensorMap m_wqkv, m_wo, m_w1, m_w2;   // box 128 rows: each CTA of a pair stages half of a 256-row W tile
+  CUtensorMap m_wo_256, m_w2_256;         // box 256 rows: residual+LayerNorm kernel (each CTA owns 256 output columns)
 };
 
 struct GraphKey {
@@ -142,7 +145,7 @@ struct b200mdm_engine {
   int *kvlen = nullptr, *tvec = nullptr, *action = nullptr;
   StepState* state = nullptr;
   CUtensorMap m_xin, m_h16, m_att, m_ffn, m_g16;      // A operands (loads, box 128 rows)
-  CUtensorMap m_qkv_st, m_ffn_st, m_h32_io;            // epilogue slabs (box 32 rows x 128 bytes)
+  CUtensorMap m_qkv_st, m_ffn_st, m_h32_io, m_h16_st;            // epilogue slabs (box 32 rows x 128 bytes)
   CUtensorMap m_att_q, m_att_kv, m_att_o;             // tcgen05 attention: per-sample 3-D views of qkv16 / att16
   CUtensorMap m_h32_c, m_h32_u, m_h16_c, m_h16_u;      // per-CFG-half views of h32 / h16 for the embedding epilogue
   float* pe_bias = nullptr;
@@ -193,6 +196,8 @@ static int init_kernel_attrs() {
   TRY((set_gemm2_attr<EpiBiasF16<false>>()));
   TRY((set_gemm2_attr<EpiBiasF16<true>>()));
   TRY((set_gemm2_attr<EpiResidualF32>()));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_resid_ln_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLnSmem::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(gemm2_resid_ln_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2LnSmem::TOTAL));
   TRY((set_gemm_attr<128, EpiEmbed>()));
   TRY((set_gemm_attr<96, EpiOutStep>()));
   CUDA_TRY(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -220,6 +225,34 @@ static int launch_gemm2(const CUtensorMap& a, const CUtensorMap& b, const CUtens
   const int max_clusters = num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   gemm2_f16_tcgen05<Epi><<<2 * clusters, GEMM_THREADS, Gemm2Smem<Epi>::TOTAL, s>>>(a, b, c, M, N, K, p);
+  CUDA_TRY(cudaGetLastError());
+  return B200MDM_OK;
+}
+
+// h <- LayerNorm(h + A W^T + bias), 2-CTA cluster splitting the 512 columns, LayerNorm statistics exchanged through
+// distributed shared memory (w256: W map with box 256 rows)
+static int launch_gemm_resid_ln(const CUtensorMap& a, const CUtensorMap& w256, const CUtensorMap& h32_io, __half* h16, int M,
+                                int K, const float* bias, const float* gamma, const float* beta, cudaStream_t s,
+                                int num_sms) {
+  const int tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int max_clusters = num_sms / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  GemmLnParams lp{bias, gamma, beta, 1e-5f};
+  gemm_resid_ln_cluster<<<2 * clusters, GLN_THREADS, GemmLnSmem::TOTAL, s>>>(a, w256, h32_io, h16, M, K, lp);
+  CUDA_TRY(cudaGetLastError());
+  return B200MDM_OK;
+}
+
+static long long* g_ln_trace = nullptr;   // debug: set through b200mdm_debug_trace()
+// h <- LayerNorm(h + A W^T + bias): residual + LayerNorm fused into the CTA-pair GEMM epilogue (N = 512)
+static int launch_gemm2_resid_ln(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& h32_io,
+                                 __half* h16, int M, int K, const float* bias, const float* gamma,
+                                 const float* beta, cudaStream_t s, int num_sms) {
+  const int tiles = (M + GEMM2_TILE_M - 1) / GEMM2_TILE_M;
+  const int max_clusters = num_sms / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  LnParams lp{bias, gamma, beta, 1e-5f, g_ln_trace};
+  gemm2_resid_ln_tcgen05<<<2 * clusters, LN2_THREADS, Gemm2LnSmem::TOTAL, s>>>(a, w, h32_io, h16, M, K, lp);
   CUDA_TRY(cudaGetLastError());
   return B200MDM_OK;
 }
@@ -459,6 +492,8 @@ extern "C" int b200mdm_finalize_weights(b200mdm_engine* e, void* stream) {
     TRY(make_map(&w.m_wo, w.wo, d, d, d, 128));
     TRY(make_map(&w.m_w1, w.w1, ff, d, d, 128));
     TRY(make_map(&w.m_w2, w.w2, d, ff, ff, 128));
+    TRY(make_map(&w.m_wo_256, w.wo, d, d, d, 256));
+    TRY(make_map(&w.m_w2_256, w.w2, d, ff, ff, 256));
   }
   // timestep-embedding MLP for every model timestep: temb[t] = W2 silu(W1 pe[t] + b1) + b2
   const int R = e->cfg.temb_rows;
@@ -527,6 +562,7 @@ static int build_workspace(b200mdm_engine* e, int B, int T, int halves) {
   TRY(make_map_t(&e->m_qkv_st, e->qkv16, 2, M, 3 * d, 3 * d, 32));
   TRY(make_map_t(&e->m_ffn_st, e->ffn16, 2, M, e->ff, e->ff, 32));
   TRY(make_map_t(&e->m_h32_io, e->h32, 4, M, d, d, 32));
+  TRY(make_map_t(&e->m_h16_st, e->h16, 2, M, d, d, 32));
   if (S <= ATC_MAX_KEYS) {
     AttnMaps am;
     TRY(make_attn_maps(&am, e->qkv16, e->att16, Bp, S, d));
@@ -653,21 +689,13 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
     } else {
       TRY(launch_attention_mma(e->qkv16, e->att16, e->kvlen, e->Bp, S, d, e->H, s));
     }
-    {
-      EpiResidualF32::Params p{w.bo};
-      TRY((launch_gemm2<EpiResidualF32>(e->m_att, w.m_wo, e->m_h32_io, e->M, d, d, p, s, e->num_sms)));
-    }
-    TRY(launch_layernorm(e->h32, e->h16, w.g1, w.be1, e->M, s));
+    TRY(launch_gemm_resid_ln(e->m_att, w.m_wo_256, e->m_h32_io, e->h16, e->M, d, w.bo, w.g1, w.be1, s, e->num_sms));
     {
       EpiBiasF16<true>::Params p{w.b1};
       TRY((launch_gemm2<EpiBiasF16<true>>(e->m_h16, w.m_w1, e->m_ffn_st, e->M, ff, d, p, s, e->num_sms)));
     }
-    {
-      EpiResidualF32::Params p{w.b2};
-      TRY((launch_gemm2<EpiResidualF32>(e->m_ffn, w.m_w2, e->m_h32_io, e->M, d, ff, p, s, e->num_sms)));
-    }
-    TRY(launch_layernorm(e->h32, e->h16, w.g2, w.be2, e->M, s));
-    nk += 7;
+    TRY(launch_gemm_resid_ln(e->m_ffn, w.m_w2_256, e->m_h32_io, e->h16, e->M, ff, w.b2, w.g2, w.be2, s, e->num_sms));
+    nk += 5;
   }
   blend_split_kernel<<<(e->MB + 7) / 8, 256, 0, s>>>(e->h32, e->g16, e->scale, B, S, d, e->halves);
   CUDA_TRY(cudaGetLastError());
@@ -899,6 +927,35 @@ extern "C" int b200mdm_test_attention(const void* qkv16_dev, void* out16_dev, co
   }
   return launch_attention_mma(static_cast<const __half*>(qkv16_dev), static_cast<__half*>(out16_dev), kvlen_dev, n_samples,
                               S, d, d / ATT_DH, s);
+}
+
+extern "C" int b200mdm_test_gemm_resid_ln(const void* a16_dev, const void* w16_dev, const float* bias_dev,
+                                          const float* gamma_dev, const float* beta_dev, float* h32_dev, void* h16_dev,
+                                          int32_t M, int32_t K, int32_t impl, void* stream) {
+  if (!a16_dev || !w16_dev || !bias_dev || !gamma_dev || !beta_dev || !h32_dev || !h16_dev || M <= 0 || K <= 0 || K % 8)
+    return fail(B200MDM_EINVAL, "bad argument");
+  TRY(init_kernel_attrs());
+  int dev = 0, sms = 148;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CUtensorMap ma, mb, m32;
+  TRY(make_map(&ma, a16_dev, M, K, K, GEMM_BLOCK_M));
+  if (impl == 0) {
+    TRY(make_map(&mb, w16_dev, LN_D, K, K, 256));
+    TRY(make_map_t(&m32, h32_dev, 4, M, LN_D, LN_D, 32));
+    return launch_gemm_resid_ln(ma, mb, m32, static_cast<__half*>(h16_dev), M, K, bias_dev, gamma_dev, beta_dev,
+                                static_cast<cudaStream_t>(stream), sms);
+  }
+  TRY(make_map(&mb, w16_dev, LN_D, K, K, 128));
+  TRY(make_map_t(&m32, h32_dev, 4, M, LN_D, LN_D, 32));
+  return launch_gemm2_resid_ln(ma, mb, m32, static_cast<__half*>(h16_dev), M, K, bias_dev, gamma_dev, beta_dev, static_cast<cudaStream_t>(stream), sms);
+}
+
+// Debug aid (not part of the public header): device buffer of 32 int64 that receives clock64 stamps of the fused
+// residual+LayerNorm kernel (block 0, first epilogue warp): tile start, accumulator ready, pass 1 done, stats done, pass 2 done.
+extern "C" int b200mdm_debug_trace(long long* dev_buf) {
+  g_ln_trace = dev_buf;
+  return B200MDM_OK;
 }
 
 extern "C" int b200mdm_test_layernorm(float* h32_dev, void* h16_dev, const float* gamma_dev, const float* beta_dev,

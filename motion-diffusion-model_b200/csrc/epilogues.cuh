@@ -68,24 +68,28 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // box {64 cols, 32 rows}, SWIZZLE_128B.
 template <bool GELU>
 struct EpiBiasF16 {
-  static constexpr int SMEM_PER_WARP = 2 * 4096 + 1024;  // two output slabs + the tile's bias
+  // one output slab + the tile's bias: with 8 epilogue warps the wait for the previous slab's TMA store overlaps the
+  // other warps' work, and the 4 KB saved per warp buy one more operand pipeline stage (the layer GEMMs are bound
+  // by operand bytes in flight)
+  static constexpr int NSLAB = (GEMM_EPI_WARPS == 8) ? 1 : 2;
+  static constexpr int SMEM_PER_WARP = NSLAB * 4096 + 1024;
   static constexpr bool RELEASE_EARLY = true;
   struct Params {
     const float* bias;
   };
   static __device__ __forceinline__ void tile_begin(EpiCtx& ctx, const Params& p, int, int col_base) {
-    stage_bias(reinterpret_cast<float*>(ctx.smem + 8192), p.bias, col_base, ctx.N, ctx.lane);
+    stage_bias(reinterpret_cast<float*>(ctx.smem + NSLAB * 4096), p.bias, col_base, ctx.N, ctx.lane);
   }
   static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0,
                                                int) {
     const int half = (col0 >> 5) & 1;
-    uint8_t* slab = ctx.smem + (ctx.seq & 1) * 4096;
+    uint8_t* slab = ctx.smem + (ctx.seq % NSLAB) * 4096;
     if (half == 0) {
-      // the store issued two slabs ago read this buffer: make sure it has finished reading
-      if (ctx.lane == 0) bulk_wait_group_read<1>();
+      // the store that last read this buffer (NSLAB slabs ago) must have finished reading
+      if (ctx.lane == 0) bulk_wait_group_read<NSLAB - 1>();
       __syncwarp();
     }
-    const float* bs = reinterpret_cast<const float*>(ctx.smem + 8192) + (col0 - ctx.col_base);
+    const float* bs = reinterpret_cast<const float*>(ctx.smem + NSLAB * 4096) + (col0 - ctx.col_base);
     uint32_t pk[16];
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -301,32 +305,35 @@ struct EpiOutStep {
     // x_out may alias x_t (in-place loop): batch every load of the chunk before the first store so that they are
     // all in flight together (consecutive lanes = consecutive frames => each load/store is one coalesced line)
     const size_t base = static_cast<size_t>(b) * p.J * p.T + t;
-    float xv[32], nv[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = col0 + j;
-      xv[j] = (p.mode != 0 && col < p.J) ? p.x_t[base + static_cast<size_t>(col) * p.T] : 0.f;
-      nv[j] = (p.mode != 0 && col < p.J) ? nz[static_cast<size_t>(col) * p.T + t] : 0.f;
-    }
+    for (int h = 0; h < 32; h += 16) {
+      float xv[16], nv[16];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = col0 + j;
-      if (col < p.J) {
-        const size_t idx = base + static_cast<size_t>(col) * p.T;
-        float x0 = __uint_as_float(raw[j]) + __ldg(p.bias + col);
-        if (p.inpaint_mask != nullptr && p.inpaint_mask[idx]) x0 = p.inpaint_motion[idx];
-        if (p.clip_denoised) x0 = fminf(fmaxf(x0, -1.f), 1.f);
-        if (p.pred_xstart != nullptr) p.pred_xstart[idx] = x0;
-        float o = x0;
-        if (p.mode == 1) {
-          const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xv[j]));
-          o = __fadd_rn(mean, __fmul_rn(sg, nv[j]));
-        } else if (p.mode == 2) {
-          const float eh = __fdiv_rn(__fsub_rn(__fmul_rn(sr, xv[j]), x0), srm1);
-          const float mean = __fadd_rn(__fmul_rn(x0, sq), __fmul_rn(ce, eh));
-          o = __fadd_rn(mean, __fmul_rn(sg, nv[j]));
+      for (int j = 0; j < 16; ++j) {
+        const int col = col0 + h + j;
+        xv[j] = (p.mode != 0 && col < p.J) ? p.x_t[base + static_cast<size_t>(col) * p.T] : 0.f;
+        nv[j] = (p.mode != 0 && col < p.J) ? nz[static_cast<size_t>(col) * p.T + t] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int col = col0 + h + j;
+        if (col < p.J) {
+          const size_t idx = base + static_cast<size_t>(col) * p.T;
+          float x0 = __uint_as_float(raw[h + j]) + __ldg(p.bias + col);
+          if (p.inpaint_mask != nullptr && p.inpaint_mask[idx]) x0 = p.inpaint_motion[idx];
+          if (p.clip_denoised) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+          if (p.pred_xstart != nullptr) p.pred_xstart[idx] = x0;
+          float o = x0;
+          if (p.mode == 1) {
+            const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xv[j]));
+            o = __fadd_rn(mean, __fmul_rn(sg, nv[j]));
+          } else if (p.mode == 2) {
+            const float eh = __fdiv_rn(__fsub_rn(__fmul_rn(sr, xv[j]), x0), srm1);
+            const float mean = __fadd_rn(__fmul_rn(x0, sq), __fmul_rn(ce, eh));
+            o = __fadd_rn(mean, __fmul_rn(sg, nv[j]));
+          }
+          p.x_out[idx] = o;
         }
-        p.x_out[idx] = o;
       }
     }
   }

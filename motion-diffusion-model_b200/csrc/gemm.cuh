@@ -20,7 +20,15 @@ namespace b200 {
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;  // 64 fp16 = 128 B = one swizzle row
-constexpr int GEMM_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each owning every other 64-column block
+#ifndef B200_GEMM_EPI_WARPS
+#define B200_GEMM_EPI_WARPS 8
+#endif
+// Epilogue warps per CTA: 4 (one per TMEM lane quarter) or 8 (two per quarter, each owning every other 64-column
+// block).  Measured on B200: 8 warps do not shorten the layer GEMMs (they are bound by operand bytes in flight, i.e.
+// by pipeline depth x L2 latency), while 4 warps leave shared memory for one more pipeline stage.
+constexpr int GEMM_EPI_WARPS = B200_GEMM_EPI_WARPS;
+constexpr int GEMM_EPI_PARTS = GEMM_EPI_WARPS / 4;
+static_assert(GEMM_EPI_WARPS == 4 || GEMM_EPI_WARPS == 8, "4 or 8 epilogue warps");
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_BAR_BYTES = 512;
 
@@ -57,7 +65,7 @@ struct EpiCtx {
 // `release` (accumulator free) runs as soon as this warp's last TMEM read has landed.
 template <int BLOCK_N>
 __device__ __forceinline__ int epi_next_chunk(int c) {
-  return ((c & 32) == 0 && c + 32 < BLOCK_N) ? c + 32 : (c & ~63) + 128;
+  return ((c & 32) == 0 && c + 32 < BLOCK_N) ? c + 32 : (c & ~63) + 64 * GEMM_EPI_PARTS;
 }
 template <int BLOCK_N, class Epi, class Release>
 __device__ __forceinline__ void epilogue_tile(EpiCtx& ctx, const typename Epi::Params& ep, uint32_t taddr, int row0,

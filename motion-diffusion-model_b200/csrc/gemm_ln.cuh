@@ -1,0 +1,301 @@
+// tcgen05 GEMM with residual add + LayerNorm fused into the epilogue, N = d_model = 512 split over a 2-CTA cluster:
+//
+//     h <- LayerNorm( h + A W^T + bias ; gamma, beta, eps )        in place on h32 (fp32) + fp16 copy h16
+//     (post-norm nn.TransformerEncoderLayer of the reference, built at model/mdm.py:77-84)
+//
+// Both CTAs of a cluster work on the SAME 128 rows; CTA r owns columns [256 r, 256 r + 256) (its own 256 rows of W,
+// cta_group::1 MMAs, 128 x 256 accumulator).  Each CTA therefore needs only 256 TMEM columns per tile and keeps TWO
+// accumulator stages, so the two-pass LayerNorm epilogue of tile i overlaps the MMAs of tile i+1 -- and the epilogue
+// traffic (one read + 1.5 writes of the residual stream per LayerNorm) is spread over the whole kernel instead of
+// arriving in chip-wide bursts.
+//
+// Epilogue, thread = row, warps (q = lane quarter, part = 128-column half of the CTA's 256 columns):
+//   pass 1    v = acc + bias + residual (TMA-loaded slabs); per-row partial sum / sum of squares; v -> TMEM (in place)
+//   exchange  partials of the two parts meet in shared memory (named barrier); the part-0 warp pushes the CTA's partial
+//             into the PEER CTA's shared memory (st.shared::cluster) and signals the peer's mbarrier; both CTAs now own
+//             the statistics of the complete 512-wide rows
+//   pass 2    y = (v - mean) rstd gamma + beta -> fp32 slab -> TMA store (h32) ; fp16 -> 256-bit st.global (h16)
+// (measured: TMA slabs for the fp32 stream beat direct 256-bit loads/stores, 43.8 / 51.8 us vs 52.0 / 59.7 us per launch)
+#pragma once
+#include "epilogues.cuh"
+#include "gemm.cuh"
+
+namespace b200 {
+
+constexpr int GLN_EPI_WARPS = 8;    // two warps per TMEM lane quarter, one per column half
+constexpr int GLN_THREADS = 64 + 32 * GLN_EPI_WARPS;
+
+constexpr int GLN_D = 512;
+constexpr int GLN_BN = 256;                       // columns per CTA
+constexpr int GLN_WARP_SMEM = 8 * 1024;           // two fp32 slabs per epilogue warp (residual in / normalised out)
+constexpr int GLN_STAGE_BYTES = (128 + GLN_BN) * GEMM_BLOCK_K * 2;   // 48 KB
+constexpr int GLN_AUX_BYTES = 3 * GLN_BN * 4 /*bias gamma beta*/ + 3 * 2048 /*local, remote, total stats*/ + 1024 /*barriers*/;
+
+struct GemmLnSmem {
+  static constexpr int EPI_BYTES = GLN_EPI_WARPS * GLN_WARP_SMEM;
+  static constexpr int budget = 227 * 1024 - 1024 - EPI_BYTES - GLN_AUX_BYTES;
+  static constexpr int STAGES = (budget / GLN_STAGE_BYTES) > 6 ? 6 : (budget / GLN_STAGE_BYTES);
+  static constexpr int TOTAL = 1024 + STAGES * GLN_STAGE_BYTES + EPI_BYTES + GLN_AUX_BYTES;
+  static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
+};
+
+struct GemmLnParams {
+  const float* bias;    // [512]
+  const float* gamma;   // [512]
+  const float* beta;    // [512]
+  float eps;
+};
+
+// map_a: A [M, K] fp16, box 128 rows; map_b: W [512, K] fp16, box 256 rows; map_h32: h32 [M, 512] fp32, box 32 x 32
+// (loaded and stored in place); h16 [M, 512] fp16
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GLN_THREADS, 1)
+gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ CUtensorMap map_h32, __half* __restrict__ h16, int M, int K,
+                      const GemmLnParams lp) {
+  using SM = GemmLnSmem;
+  constexpr int STAGES = SM::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  uint8_t* epi_smem = smem + STAGES * GLN_STAGE_BYTES;
+  float* prm = reinterpret_cast<float*>(epi_smem + SM::EPI_BYTES);                 // bias | gamma | beta  (this CTA's 256 cols)
+  float2* st_local = reinterpret_cast<float2*>(prm + 3 * GLN_BN);                  // [stage 2][q 4][part 2][lane 32] -> 4 KB? no: see below
+  // layout of the 6 KB statistics area: local [2][4][2][32] float2 would be 4 KB; we keep [2 stages][4 q][32] per array
+  // and let part p of a quarter use array p (local0 / local1), plus remote and total:
+  float2* st_part0 = st_local;                     // [2][4][32]
+  float2* st_part1 = st_local + 256;               // [2][4][32]
+  float2* st_remote = st_local + 512;              // [2][4][32]  written by the PEER CTA
+  // (total is recomputed by each warp from part0 + part1 + remote, no extra array needed)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(st_local + 768);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;             // [STAGES]
+  uint64_t* acc_full = bars + 2 * STAGES;          // [2]
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;     // [2]
+  uint64_t* xbar = bars + 2 * STAGES + 4;          // [2 stages][4 q]  peer's statistics have landed
+  uint64_t* rbar = xbar + 8;                       // [GLN_EPI_WARPS][2] residual slabs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + GLN_EPI_WARPS * 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;   // one tile per cluster = 128 rows x 512 columns
+  const int num_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  const int col_cta = static_cast<int>(rank) * GLN_BN;
+
+  for (int i = threadIdx.x; i < GLN_BN; i += blockDim.x) {
+    prm[i] = lp.bias[col_cta + i];
+    prm[GLN_BN + i] = lp.gamma[col_cta + i];
+    prm[2 * GLN_BN + i] = lp.beta[col_cta + i];
+  }
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_h32);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], GLN_EPI_WARPS);
+    }
+    for (int s = 0; s < 8; ++s) mbar_init(&xbar[s], 32);   // the 32 lanes of the peer's part-0 warp of that quarter
+    for (int s = 0; s < GLN_EPI_WARPS * 2; ++s) mbar_init(&rbar[s], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers exist before anybody signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = tiles + stage * GLN_STAGE_BYTES;
+          uint8_t* sb = sa + 16384;
+          mbar_expect_tx(&full_bar[stage], GLN_STAGE_BYTES);
+          tma_load_2d(sa, &map_a, &full_bar[stage], kb * GEMM_BLOCK_K, tile * GEMM_BLOCK_M);
+          tma_load_2d(sb, &map_b, &full_bar[stage], kb * GEMM_BLOCK_K, col_cta);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_f16(GEMM_BLOCK_M, GLN_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int as = it & 1;
+        mbar_wait(&acc_empty[as], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + stage * GLN_STAGE_BYTES);
+          const uint64_t da = umma_desc_k_sw128(sa);
+          const uint64_t db = umma_desc_k_sw128(sa + 16384);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) umma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (2..9)
+    const int q = warp & 3;
+    const int part = (warp - 2) >> 2;                 // 128-column half of this CTA's 256 columns
+    uint8_t* wsm = epi_smem + (warp - 2) * GLN_WARP_SMEM;
+    uint8_t* slab[2] = {wsm, wsm + 4096};
+    uint64_t* rb = rbar + (warp - 2) * 2;
+    uint32_t rseq = 0;                                // residual slabs consumed (buffer = rseq & 1, parity = (rseq >> 1) & 1)
+    const int colw = part * 128;                      // first column of this warp inside the CTA's 256
+    const float* bias_s = prm + colw;
+    const float* gamma_s = prm + GLN_BN + colw;
+    const float* beta_s = prm + 2 * GLN_BN + colw;
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int row0 = tile * GEMM_BLOCK_M + q * 32;
+      const bool live = row0 < M;
+      const int gcol = col_cta + colw;                // first global column of this warp
+      const uint32_t taddr = tmem_base + as * 256 + (static_cast<uint32_t>(q * 32) << 16) + colw;
+      auto load_resid = [&](uint32_t seq, int c) {
+        if (lane == 0) {
+          bulk_wait_group_read<0>();                  // stores out of these slabs (previous tile, pass 2) have been read
+          mbar_expect_tx(&rb[seq & 1], 4096);
+          tma_load_2d(slab[seq & 1], &map_h32, &rb[seq & 1], gcol + 32 * c, row0);
+        }
+      };
+      if (live) {
+        load_resid(rseq, 0);
+        load_resid(rseq + 1, 1);
+      }
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      float sum = 0.f, sumsq = 0.f;
+      if (live) {
+        // ---- pass 1
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t raw[32];
+          tmem_ld_32x32(taddr + 32 * c, raw);
+          mbar_wait(&rb[rseq & 1], (rseq >> 1) & 1);
+          tmem_ld_wait();
+          const uint8_t* sl = slab[rseq & 1];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 r = *reinterpret_cast<const float4*>(sl + slab_off(lane, j));
+            const float4 b = *reinterpret_cast<const float4*>(bias_s + 32 * c + 4 * j);
+            const float v0 = r.x + (__uint_as_float(raw[4 * j + 0]) + b.x);
+            const float v1 = r.y + (__uint_as_float(raw[4 * j + 1]) + b.y);
+            const float v2 = r.z + (__uint_as_float(raw[4 * j + 2]) + b.z);
+            const float v3 = r.w + (__uint_as_float(raw[4 * j + 3]) + b.w);
+            sum += (v0 + v1) + (v2 + v3);
+            sumsq = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, sumsq))));
+            raw[4 * j + 0] = __float_as_uint(v0);
+            raw[4 * j + 1] = __float_as_uint(v1);
+            raw[4 * j + 2] = __float_as_uint(v2);
+            raw[4 * j + 3] = __float_as_uint(v3);
+          }
+          tmem_st_32x32(taddr + 32 * c, raw);
+          __syncwarp();
+          if (c + 2 < 4) load_resid(rseq + 2, c + 2);
+          ++rseq;
+        }
+        tmem_st_wait();
+      }
+      // ---- statistics of the full 512-wide rows: part 0 + part 1 of this CTA + the peer CTA's 256 columns
+      const int sidx = (as * 4 + q) * 32 + lane;
+      (part == 0 ? st_part0 : st_part1)[sidx] = make_float2(sum, sumsq);
+      named_bar_sync(1 + q, 64);
+      if (part == 0) {
+        const float2 a = st_part0[sidx], b = st_part1[sidx];
+        const uint32_t peer_slot = mapa_shared(smem_u32(&st_remote[sidx]), rank ^ 1);
+        st_shared_cluster_f32x2(peer_slot, a.x + b.x, a.y + b.y);
+        mbar_arrive_remote(mapa_shared(smem_u32(&xbar[as * 4 + q]), rank ^ 1));   // release.cluster, one per lane
+      }
+      mbar_wait_cluster(&xbar[as * 4 + q], aphase);   // the peer's 32 lanes have delivered their partials
+      const float2 p0 = st_part0[sidx], p1 = st_part1[sidx], pr = st_remote[sidx];
+      const float mean = ((p0.x + p1.x) + pr.x) * (1.f / GLN_D);
+      const float var = fmaxf(((p0.y + p1.y) + pr.y) * (1.f / GLN_D) - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + lp.eps);
+      if (live) {
+        // ---- pass 2
+        if (lane == 0) bulk_wait_group_read<0>();
+        __syncwarp();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t raw[32];
+          tmem_ld_32x32(taddr + 32 * c, raw);
+          tmem_ld_wait();
+          uint8_t* o32 = slab[c & 1];
+          if (c >= 2) {
+            if (lane == 0) bulk_wait_group_read<1>();
+            __syncwarp();
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 g = *reinterpret_cast<const float4*>(gamma_s + 32 * c + 4 * j);
+            const float4 be = *reinterpret_cast<const float4*>(beta_s + 32 * c + 4 * j);
+            float4 y;
+            y.x = (__uint_as_float(raw[4 * j + 0]) - mean) * rstd * g.x + be.x;
+            y.y = (__uint_as_float(raw[4 * j + 1]) - mean) * rstd * g.y + be.y;
+            y.z = (__uint_as_float(raw[4 * j + 2]) - mean) * rstd * g.z + be.z;
+            y.w = (__uint_as_float(raw[4 * j + 3]) - mean) * rstd * g.w + be.w;
+            *reinterpret_cast<float4*>(o32 + slab_off(lane, j)) = y;
+            pk[2 * j] = pack_half2(y.x, y.y);
+            pk[2 * j + 1] = pack_half2(y.z, y.w);
+          }
+          if (row0 + lane < M) {   // fp16 copy: 64 contiguous bytes of this thread's row, two whole 32-byte sectors
+            __half* dst = h16 + static_cast<size_t>(row0 + lane) * GLN_D + gcol + 32 * c;
+            stg256(dst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+            stg256(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_h32, o32, gcol + 32 * c, row0);
+            bulk_commit_group();
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+    if (lane == 0) bulk_wait_group<0>();
+    __syncwarp();
+  }
+
+  // the peer may still be writing into this CTA's shared memory / signalling its barriers
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace b200

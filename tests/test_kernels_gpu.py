@@ -90,3 +90,25 @@ def test_layernorm(M):
     torch.cuda.synchronize()
     assert (h32 - ref).abs().max().item() < 2e-5
     assert (h16.float() - ref).abs().max().item() < 4e-3
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("M,K", [(256, 512), (25216 // 4, 512), (3000, 1024), (130, 512), (77, 1024), (25216, 512)])
+def test_gemm_residual_layernorm_fused(M, K, impl):
+    """h <- LN(h + A W^T + b): the fused out-projection / FFN-down kernel vs torch fp32."""
+    L, lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    a = torch.randn(M, K, device="cuda", generator=g).half()
+    w = (torch.randn(512, K, device="cuda", generator=g) / K ** 0.5).half()
+    bias = torch.randn(512, device="cuda", generator=g) * 0.1
+    gamma = 1 + 0.1 * torch.randn(512, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(512, device="cuda", generator=g)
+    h = torch.randn(M, 512, device="cuda", generator=g) * 1.5 + 0.2
+    ref = torch.nn.functional.layer_norm(h + a.float() @ w.float().t() + bias, (512,), gamma, beta, 1e-5)
+    h32 = h.clone()
+    h16 = torch.full((M, 512), float("nan"), device="cuda", dtype=torch.float16)
+    L.check(lib.b200mdm_test_gemm_resid_ln(_p(a), _p(w), _p(bias), _p(gamma), _p(beta), _p(h32), _p(h16), M, K, impl, _stream()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(h32).all() and torch.isfinite(h16.float()).all()
+    assert (h32 - ref).abs().max().item() < 2e-4
+    assert (h16.float() - ref).abs().max().item() < 5e-3
