@@ -277,34 +277,62 @@ def main():
 
     line = None
     if rank == 0:
-        # ---- dominant kernel alone: tcgen05 GEMM at the FFN-up shape of this workload (M = 128 seq x 197 tok)
+        # ---- the step's kernels timed alone at this workload's shapes (M = 128 sequences x 197 tokens), through the
+        # kernel-level C-ABI hooks, CUDA events on the launching stream, L2 flushed between launches.  "roofline" is
+        # the kernel with the largest share of the step (profiles/: gemm_resid_ln_cluster, FFN-down shape).
         import ctypes
         from b200mdm import _lib
         lib = _lib.load()
-        M, N, K = 2 * B * (T + 1), FF, D
-        A = torch.randn(M, K, device=dev).half()
-        Wt = torch.randn(N, K, device=dev).half()
-        bias = torch.zeros(N, device=dev)
-        O = torch.empty(M, N, device=dev, dtype=torch.float16)
+        M = 2 * B * (T + 1)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        call = lambda: _lib.check(lib.b200mdm_test_gemm_f16(A.data_ptr(), Wt.data_ptr(), bias.data_ptr(), O.data_ptr(), M, N, K, 1, 256, st))
-        for _ in range(3):
-            call()
-        ts = []
-        for _ in range(10):
-            flush.zero_()                                              # L2 flush between timed launches
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); call(); e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        k_ms = sum(ts) / len(ts)
-        k_tflops = 2.0 * M * N * K / (k_ms * 1e-3) / 1e12
-        path_tflops = value * FLOP_PER_MOTION / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_f16_tcgen05<256,EpiBiasF16<gelu>> M=%d N=%d K=%d" % (M, N, K),
+
+        def time_kernel(call):
+            for _ in range(3):
+                call()
+            ts = []
+            for _ in range(10):
+                flush.zero_()                                          # L2 flush between timed launches
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); call(); e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            return sum(ts) / len(ts)
+
+        def gemm_case(N, K, act):
+            A = torch.randn(M, K, device=dev).half()
+            Wt = (torch.randn(N, K, device=dev) / K ** 0.5).half()
+            bias = torch.zeros(N, device=dev)
+            O = torch.empty(M, N, device=dev, dtype=torch.float16)
+            ms = time_kernel(lambda: _lib.check(lib.b200mdm_test_gemm_f16(A.data_ptr(), Wt.data_ptr(), bias.data_ptr(), O.data_ptr(), M, N, K, act, 512, st)))
+            return 2.0 * M * N * K / (ms * 1e-3) / 1e12, ms
+
+        def ln_case(K):
+            A = torch.randn(M, K, device=dev).half()
+            Wt = (torch.randn(512, K, device=dev) / K ** 0.5).half()
+            vec = [torch.zeros(512, device=dev), torch.ones(512, device=dev), torch.zeros(512, device=dev)]
+            h32 = torch.randn(M, 512, device=dev)
+            h16 = torch.empty(M, 512, device=dev, dtype=torch.float16)
+            ms = time_kernel(lambda: _lib.check(lib.b200mdm_test_gemm_resid_ln(A.data_ptr(), Wt.data_ptr(), vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), h32.data_ptr(), h16.data_ptr(), M, K, 0, st)))
+            return 2.0 * M * 512 * K / (ms * 1e-3) / 1e12, ms
+
+        k_tflops, k_ms = ln_case(FF)
+        others = []
+        for name, fn in (("gemm_resid_ln_cluster out-proj K=512", lambda: ln_case(D)),
+                         ("gemm2_f16_tcgen05<bias> QKV N=1536 K=512", lambda: gemm_case(3 * D, D, 0)),
+                         ("gemm2_f16_tcgen05<bias,gelu> FFN-up N=1024 K=512", lambda: gemm_case(FF, D, 1))):
+            tf, ms_k = fn()
+            others.append({"kernel": name, "achieved": round(tf, 1), "frac": round(tf / peaks["burst"], 4), "us": round(ms_k * 1e3, 1)})
+        path_tflops = value / world * FLOP_PER_MOTION / 1e12            # per GPU
+        roof = {"bound": "tensor", "kernel": "gemm_resid_ln_cluster (FFN-down + residual + LayerNorm) M=%d N=512 K=%d" % (M, FF),
                 "achieved": round(k_tflops, 1), "peak": peaks["burst"], "unit": "TFLOP/s",
-                "frac": round(k_tflops / peaks["burst"], 4), "traffic": None, "peak_source": peaks["source"] + " bf16 burst",
-                "path_achieved_tflops": round(path_tflops, 1), "path_frac_of_sustained": round(path_tflops / peaks["sustained"], 4)}
+                "frac": round(k_tflops / peaks["burst"], 4),
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the ncu --set full
+                # capture committed as profiles/r01_b_top_kernel_ncu_metrics.txt (104.4 MB + 22.6 MB)
+                "traffic": 127.06e6, "us": round(k_ms * 1e3, 1),
+                "peak_source": peaks["source"] + " bf16 burst (cuBLAS 8192^3)", "other_kernels": others,
+                "path_achieved_tflops_per_gpu": round(path_tflops, 1),
+                "path_frac_of_sustained": round(path_tflops / peaks["sustained"], 4)}
         log("kernel roofline timed: %.1f TFLOP/s" % k_tflops)
         cpu = None
         if world == 1 and not a.no_cpu_baseline:

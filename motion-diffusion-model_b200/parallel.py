@@ -1,0 +1,95 @@
+"""Batch-of-prompts data parallelism over the GPUs of one box.
+
+Samples never interact inside the sampling loop (attention is per sample, LayerNorm per token), so the batch is cut
+into contiguous per-rank slices; the ONLY collective of the path is one broadcast of the cached text embedding
+(the reference encodes the prompts once per loop, diffusion/gaussian_diffusion.py:633-635), plus an optional gather
+of the finished motions.  Nothing crosses GPUs inside the loop.
+
+Determinism: with ``noise_mode="global"`` every rank draws the SAME global noise stream (same generator seed) and
+keeps its slice, so the G-GPU result is bitwise identical to the 1-GPU result for that seed.
+``noise_mode="per_rank"`` draws only the local slice (rank-dependent stream; cheaper for 1000-step loops).
+
+One process per GPU, ``torch.distributed`` (backend nccl on GPUs; the same code runs on gloo/CPU in the tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(global_batch, rank, world):
+    """Contiguous slice [lo, hi) of rank `rank`; the first (global_batch % world) ranks get one extra sample."""
+    base, extra = divmod(global_batch, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def broadcast_text_embed(text_embed, src=0, group=None):
+    """The one collective of the path: rank `src` owns the encoded prompts [1, B, C]; everybody receives them."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(text_embed, src=src, group=group)
+    return text_embed
+
+
+_BATCH_KEYS = ("mask", "lengths", "scale", "action", "inpainting_mask", "inpainted_motion", "prefix")
+
+
+def shard_model_kwargs(model_kwargs, lo, hi):
+    """Slice the reference's `y` dict (data_loaders/tensors.py:22-64 schema) along the batch dimension."""
+    y = model_kwargs["y"]
+    out = {}
+    for k, v in y.items():
+        if k == "text_embed" and torch.is_tensor(v):
+            out[k] = v[:, lo:hi].contiguous() if v.shape[1] > 1 else v      # [1, B, C]; a single prompt is shared
+        elif k in _BATCH_KEYS and torch.is_tensor(v):
+            out[k] = v[lo:hi].contiguous()
+        elif k in ("text", "tokens") and isinstance(v, (list, tuple)):
+            out[k] = list(v[lo:hi])
+        else:
+            out[k] = v
+    return {**model_kwargs, "y": out}
+
+
+def sample_sharded(sample_fn, model, shape, model_kwargs, *, n_steps, noise_mode="global", seed=None, device=None,
+                   gather=True, group=None, **kwargs):
+    """Run `sample_fn` (e.g. ``diffusion.p_sample_loop``) on this rank's slice of the batch.
+
+    shape: GLOBAL shape (B, J, F, T).  `model_kwargs['y']['text_embed']` needs to be valid on rank 0 only (it is
+    broadcast); the other entries must be present on every rank.  Returns the gathered [B, J, F, T] tensor on every
+    rank when `gather` (all_gather), else the local slice.
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B = int(shape[0])
+    lo, hi = shard_range(B, rank, world)
+    y = model_kwargs["y"]
+    if torch.is_tensor(y.get("text_embed")):
+        broadcast_text_embed(y["text_embed"], 0, group)
+    local_kwargs = shard_model_kwargs(model_kwargs, lo, hi)
+    local_shape = (hi - lo,) + tuple(shape[1:])
+    if device is None:
+        device = y["text_embed"].device if torch.is_tensor(y.get("text_embed")) else torch.device("cpu")
+    gen = None
+    if seed is not None:
+        gen = torch.Generator(device=device)
+        gen.manual_seed(seed if noise_mode == "global" else seed + 7919 * rank)
+    if noise_mode == "global":
+        # identical stream on every rank, in the reference's draw order: x_T, then one eps per step
+        x_T = torch.randn(tuple(shape), device=device, generator=gen)[lo:hi].contiguous()
+        tape = torch.empty((n_steps,) + local_shape, device=device)
+        for k in range(n_steps):
+            tape[k] = torch.randn(tuple(shape), device=device, generator=gen)[lo:hi]
+    elif noise_mode == "per_rank":
+        x_T = torch.randn(local_shape, device=device, generator=gen)
+        tape = torch.randn((n_steps,) + local_shape, device=device, generator=gen)
+    else:
+        raise ValueError("noise_mode must be 'global' or 'per_rank'")
+    local = sample_fn(model, local_shape, noise=x_T, model_kwargs=local_kwargs, noise_tape=tape, **kwargs)
+    if not gather or world == 1:
+        return local
+    # all_gather wants equal shapes: pad every shard to the largest one, trim after the exchange
+    sizes = [h - l for l, h in (shard_range(B, r, world) for r in range(world))]
+    top = max(sizes)
+    padded = torch.zeros((top,) + tuple(shape[1:]), device=local.device, dtype=local.dtype)
+    padded[: hi - lo] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
