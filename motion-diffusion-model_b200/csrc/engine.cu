@@ -210,6 +210,7 @@ static int init_kernel_attrs() {
 template <int BN, class Epi>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int M, int N, int K,
                        const typename Epi::Params& p, cudaStream_t s, int num_sms) {
+  if (N * 4 > GEMM_BIAS_BYTES) return fail(B200MDM_ENOTIMPL, "GEMM epilogue vectors are staged for N <= %d", GEMM_BIAS_BYTES / 4);
   const int tiles = ((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
   gemm_f16_tcgen05<BN, Epi><<<grid, GEMM_THREADS, GemmSmem<BN, Epi>::TOTAL, s>>>(a, b, c, M, N, K, p);
@@ -221,6 +222,7 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
 template <class Epi>
 static int launch_gemm2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int M, int N, int K,
                         const typename Epi::Params& p, cudaStream_t s, int num_sms) {
+  if (N * 4 > GEMM_BIAS_BYTES) return fail(B200MDM_ENOTIMPL, "GEMM epilogue vectors are staged for N <= %d", GEMM_BIAS_BYTES / 4);
   const int tiles = ((M + GEMM2_TILE_M - 1) / GEMM2_TILE_M) * ((N + GEMM2_BLOCK_N - 1) / GEMM2_BLOCK_N);
   const int max_clusters = num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
@@ -955,6 +957,7 @@ extern "C" int b200mdm_test_gemm_resid_ln(const void* a16_dev, const void* w16_d
 // residual+LayerNorm kernel (block 0, first epilogue warp): tile start, accumulator ready, pass 1 done, stats done, pass 2 done.
 extern "C" int b200mdm_debug_trace(long long* dev_buf) {
   g_ln_trace = dev_buf;
+  CUDA_TRY(cudaMemcpyToSymbol(g_gemm2_trace, &dev_buf, sizeof(dev_buf)));
   return B200MDM_OK;
 }
 

@@ -71,15 +71,18 @@ struct EpiBiasF16 {
   // one output slab + the tile's bias: with 8 epilogue warps the wait for the previous slab's TMA store overlaps the
   // other warps' work, and the 4 KB saved per warp buy one more operand pipeline stage (the layer GEMMs are bound
   // by operand bytes in flight)
-  static constexpr int NSLAB = (GEMM_EPI_WARPS == 8) ? 1 : 2;
-  static constexpr int SMEM_PER_WARP = NSLAB * 4096 + 1024;
+  static constexpr int NSLAB = 1;
+  static constexpr int SMEM_PER_WARP = NSLAB * 4096;
   static constexpr bool RELEASE_EARLY = true;
   struct Params {
     const float* bias;
   };
-  static __device__ __forceinline__ void tile_begin(EpiCtx& ctx, const Params& p, int, int col_base) {
-    stage_bias(reinterpret_cast<float*>(ctx.smem + NSLAB * 4096), p.bias, col_base, ctx.N, ctx.lane);
+  // the bias of ALL N columns is staged once per CTA (a per-tile global load sat on the epilogue's critical path:
+  // 1-2.7 k cycles between "accumulator ready" and the first chunk, measured with clock64 stamps)
+  static __device__ __forceinline__ void preload(const Params& p, float* dst, int N, int tid, int nthreads) {
+    for (int i = tid; i < N; i += nthreads) dst[i] = p.bias[i];
   }
+  static __device__ __forceinline__ void tile_begin(EpiCtx&, const Params&, int, int) {}
   static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0,
                                                int) {
     const int half = (col0 >> 5) & 1;
@@ -89,7 +92,7 @@ struct EpiBiasF16 {
       if (ctx.lane == 0) bulk_wait_group_read<NSLAB - 1>();
       __syncwarp();
     }
-    const float* bs = reinterpret_cast<const float*>(ctx.smem + NSLAB * 4096) + (col0 - ctx.col_base);
+    const float* bs = ctx.bias_all + col0;   // rows past N are never read: chunk() is only called for col0 < N, N % 32 == 0 here
     uint32_t pk[16];
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -129,7 +132,7 @@ struct EpiBiasF16 {
 // registers, write back into the same slab, TMA store.  map_c: fp32 [M, N], box {32 cols, 32 rows}, SWIZZLE_128B.
 struct EpiResidualF32 {
   static constexpr int NBUF = 2;
-  static constexpr int SMEM_PER_WARP = NBUF * 4096 + 1024;  // two residual/output slabs + the tile's bias
+  static constexpr int SMEM_PER_WARP = NBUF * 4096;  // two residual/output slabs
   static constexpr bool RELEASE_EARLY = true;
   struct Params {
     const float* bias;
@@ -145,7 +148,9 @@ struct EpiResidualF32 {
   }
   static __device__ __forceinline__ void tile_begin(EpiCtx& ctx, const Params& p, int row0, int col_base) {
     // NOTE: tile_begin does not know which column block this warp starts with; chunk() of the first chunk issues it
-    stage_bias(reinterpret_cast<float*>(ctx.smem + NBUF * 4096), p.bias, col_base, ctx.N, ctx.lane);
+  }
+  static __device__ __forceinline__ void preload(const Params& p, float* dst, int N, int tid, int nthreads) {
+    for (int i = tid; i < N; i += nthreads) dst[i] = p.bias[i];
   }
   static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0,
                                                int next_col0) {
@@ -156,7 +161,7 @@ struct EpiResidualF32 {
     }
     if (next_col0 >= 0) prefetch(ctx, ctx.seq + 1, row0, next_col0); else ctx.primed = false;
     uint8_t* slab = ctx.smem + b * 4096;
-    const float* bs = reinterpret_cast<const float*>(ctx.smem + NBUF * 4096) + (col0 - ctx.col_base);
+    const float* bs = ctx.bias_all + col0;
     mbar_wait(&ctx.bars[b], (ctx.seq / NBUF) & 1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -195,6 +200,7 @@ struct EpiResidualF32 {
 struct EpiEmbed {
   static constexpr int SMEM_PER_WARP = 4 * 4096;  // 2 fp32 slabs + 2 fp16 slabs
   static constexpr bool RELEASE_EARLY = true;
+  template <class P> static __device__ __forceinline__ void preload(const P&, float*, int, int, int) {}
   struct Params {
     CUtensorMap h32_c, h32_u, h16_c, h16_u;  // [B*S, d] views of the two halves, box 32 rows x 128 bytes
     const float* pe_bias;                     // [S, d] = pe[s] + bias
@@ -270,6 +276,7 @@ struct StepState {
 struct EpiOutStep {
   static constexpr int SMEM_PER_WARP = 1024;  // unused
   static constexpr bool RELEASE_EARLY = true;
+  template <class P> static __device__ __forceinline__ void preload(const P&, float*, int, int, int) {}
   struct Params {
     const float* bias;        // [J]
     const float* x_t;         // [B, J, T]

@@ -31,6 +31,7 @@ constexpr int GEMM_EPI_PARTS = GEMM_EPI_WARPS / 4;
 static_assert(GEMM_EPI_WARPS == 4 || GEMM_EPI_WARPS == 8, "4 or 8 epilogue warps");
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_BAR_BYTES = 512;
+constexpr int GEMM_BIAS_BYTES = 8192;   // per-column epilogue vector (bias) of the whole GEMM, staged once per CTA: N <= 2048
 
 template <int BLOCK_N, class Epi>
 struct GemmSmem {
@@ -38,9 +39,9 @@ struct GemmSmem {
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = GEMM_EPI_WARPS * Epi::SMEM_PER_WARP;  // SMEM_PER_WARP is a multiple of 1024
-  static constexpr int budget = 227 * 1024 - 1024 /*alignment slack*/ - EPI_BYTES - GEMM_BAR_BYTES;
+  static constexpr int budget = 227 * 1024 - 1024 /*alignment slack*/ - EPI_BYTES - GEMM_BIAS_BYTES - GEMM_BAR_BYTES;
   static constexpr int STAGES = (budget / STAGE_BYTES) > 6 ? 6 : (budget / STAGE_BYTES);
-  static constexpr int TOTAL = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + GEMM_BAR_BYTES;
+  static constexpr int TOTAL = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + GEMM_BIAS_BYTES + GEMM_BAR_BYTES;
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
   static_assert(Epi::SMEM_PER_WARP % 1024 == 0, "epilogue slabs must keep 1024-byte alignment (128B swizzle)");
 };
@@ -49,9 +50,11 @@ constexpr uint32_t tmem_cols_pow2(int n) { return n <= 32 ? 32u : n <= 64 ? 64u 
 
 // Per-warp epilogue context handed to the functor (lives in registers for the whole persistent loop).
 struct EpiCtx {
+  long long* trace;     // debug: per-chunk clock64 stamps (nullptr in production)
   uint8_t* smem;        // warp-private slab, Epi::SMEM_PER_WARP bytes, 1024-byte aligned
   uint64_t* bars;       // 4 warp-private mbarriers
   const CUtensorMap* map_c;
+  const float* bias_all; // CTA-shared copy of the functor's per-column vector for columns [0, N)
   int lane;
   int M, N;
   int col_base;         // first column of the tile in flight
@@ -82,9 +85,12 @@ __device__ __forceinline__ void epilogue_tile(EpiCtx& ctx, const typename Epi::P
     __syncwarp();
     if (ctx.lane == 0) release();
   };
+  int tr_i = 0;
   auto run = [&](uint32_t (&raw)[32], int c, int cn) {
+    if (ctx.trace && ctx.lane == 0) ctx.trace[tr_i++] = clock64();
     if (live && col_base + c < ctx.N)
       Epi::chunk(ctx, ep, raw, row0, col_base + c, (cn < BLOCK_N && col_base + cn < ctx.N) ? col_base + cn : -1);
+    if (ctx.trace && ctx.lane == 0) ctx.trace[tr_i++] = clock64();
   };
   uint32_t raw_a[32], raw_b[32];
   int c = part * 64;
@@ -133,7 +139,8 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
   uint8_t* epi_smem = smem + STAGES * SM::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + SM::EPI_BYTES);
+  float* bias_all = reinterpret_cast<float*>(epi_smem + SM::EPI_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + SM::EPI_BYTES + GEMM_BIAS_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* acc_full = bars + 2 * STAGES;       // [2]
@@ -149,6 +156,7 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
 
+  Epi::preload(ep, bias_all, N, threadIdx.x, blockDim.x);   // visible to the epilogue warps after the barrier below
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
@@ -230,11 +238,13 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     ctx.smem = epi_smem + (warp - 2) * Epi::SMEM_PER_WARP;
     ctx.bars = epi_bars + (warp - 2) * 4;
     ctx.map_c = &map_c;
+    ctx.bias_all = bias_all;
     ctx.lane = lane;
     ctx.M = M;
     ctx.N = N;
     ctx.seq = 0;
     ctx.primed = false;
+    ctx.trace = nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;

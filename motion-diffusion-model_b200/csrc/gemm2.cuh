@@ -19,6 +19,9 @@
 
 namespace b200 {
 
+// debug: clock64 stamps of cluster 0 (MMA issuer: 4 per tile; first epilogue warp: 3 per tile); null in production
+__device__ long long* g_gemm2_trace = nullptr;
+
 constexpr int GEMM2_BLOCK_N = 256;   // per pair: 256 x 256 output tile; per CTA: 128 rows x 256 columns of accumulator
 constexpr int GEMM2_TILE_M = 256;
 
@@ -28,9 +31,9 @@ struct Gemm2Smem {
   static constexpr int B_BYTES = 128 * GEMM_BLOCK_K * 2;  // this CTA's half (128 rows) of the W tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
   static constexpr int EPI_BYTES = GEMM_EPI_WARPS * Epi::SMEM_PER_WARP;
-  static constexpr int budget = 227 * 1024 - 1024 - EPI_BYTES - GEMM_BAR_BYTES;
+  static constexpr int budget = 227 * 1024 - 1024 - EPI_BYTES - GEMM_BIAS_BYTES - GEMM_BAR_BYTES;
   static constexpr int STAGES = (budget / STAGE_BYTES) > 6 ? 6 : (budget / STAGE_BYTES);
-  static constexpr int TOTAL = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + GEMM_BAR_BYTES;
+  static constexpr int TOTAL = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + GEMM_BIAS_BYTES + GEMM_BAR_BYTES;
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
 
@@ -48,7 +51,8 @@ gemm2_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
   uint8_t* epi_smem = smem + STAGES * SM::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + SM::EPI_BYTES);
+  float* bias_all = reinterpret_cast<float*>(epi_smem + SM::EPI_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + SM::EPI_BYTES + GEMM_BIAS_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]  (leader's copy is the live one)
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]  (each CTA waits on its own)
   uint64_t* acc_full = bars + 2 * STAGES;       // [2]       (each CTA waits on its own)
@@ -67,6 +71,7 @@ gemm2_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
 
+  Epi::preload(ep, bias_all, N, threadIdx.x, blockDim.x);   // visible to the epilogue warps after the barrier below
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
@@ -124,8 +129,11 @@ gemm2_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
+        long long* tr = (g_gemm2_trace != nullptr && cluster_id == 0 && it < 8) ? g_gemm2_trace + it * 8 : nullptr;
+        if (tr) tr[0] = clock64();
         mbar_wait_cluster(&acc_empty[as], aphase ^ 1);
         tc_fence_after();
+        if (tr) tr[1] = clock64();
         const uint32_t tmem_d = tmem_base + as * ACC_STRIDE;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait_cluster(&full_bar[stage], phase);
@@ -141,6 +149,7 @@ gemm2_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit_2cta_mc(&acc_full[as], 0b11);         // accumulator ready in both CTAs
+        if (tr) tr[2] = clock64();
       }
     }
   } else {
@@ -151,11 +160,13 @@ gemm2_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     ctx.smem = epi_smem + (warp - 2) * Epi::SMEM_PER_WARP;
     ctx.bars = epi_bars + (warp - 2) * 4;
     ctx.map_c = &map_c;
+    ctx.bias_all = bias_all;
     ctx.lane = lane;
     ctx.M = M;
     ctx.N = N;
     ctx.seq = 0;
     ctx.primed = false;
+    ctx.trace = nullptr;
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int m_blk = tile / tiles_n, n_blk = tile % tiles_n;
@@ -163,10 +174,15 @@ gemm2_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint32_t aphase = (it >> 1) & 1;
       const int row0 = m_blk * GEMM2_TILE_M + static_cast<int>(rank) * 128 + q * 32;
       const uint32_t taddr = tmem_base + as * ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
+      long long* tr = (g_gemm2_trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && it < 8) ? g_gemm2_trace + it * 8 : nullptr;
+      if (tr) tr[4] = clock64();
+      if (tr) { mbar_wait(&acc_full[as], aphase); tr[5] = clock64(); }
+      ctx.trace = (tr && it >= 2 && it < 6) ? g_gemm2_trace + 64 + (it - 2) * 16 : nullptr;
       epilogue_tile<GEMM2_BLOCK_N, Epi>(ctx, ep, taddr, row0, n_blk * GEMM2_BLOCK_N, part, &acc_full[as], aphase, [&]() {
         if (leader) mbar_arrive(&acc_empty[as]);
-        else mbar_arrive_remote(mapa_shared(smem_u32(&acc_empty[as]), 0));
+        else mbar_arrive_remote_relaxed(mapa_shared(smem_u32(&acc_empty[as]), 0));
       });
+      if (tr) tr[6] = clock64();
     }
     Epi::finish(ctx);
   }

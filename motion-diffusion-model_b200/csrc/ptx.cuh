@@ -327,6 +327,11 @@ __device__ __forceinline__ void umma_commit_2cta_mc(uint64_t* bar, uint16_t cta_
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
 }
+// Same without memory ordering (no MEMBAR): for signals that publish nothing through memory, e.g. "this warp has
+// finished reading the TMEM accumulator" (the tcgen05.ld results are already in registers, tcgen05.wait::ld done).
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t remote_bar_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
+}
 }  // namespace b200
 
 // ------------------------------------------------------------------ appended: 256-bit global accesses (sm_100)
