@@ -556,6 +556,27 @@ static int build_workspace(b200mdm_engine* e, int B, int T, int halves) {
   TRY(dalloc(&e->action, B, true));
   e->B = B; e->T = T; e->S = S; e->halves = halves; e->Bp = Bp;
   e->M = static_cast<int>(M); e->MB = static_cast<int>(MB);
+  // Keep the fp32 residual stream resident in the L2 (126 MB): it is read and rewritten by every residual+LayerNorm
+  // GEMM, and between two of them ~230 MB of other activations stream through.  The window is attached to the engine
+  // stream, so every kernel captured into the step graph inherits it.  Best effort: failures are ignored.
+  {
+    cudaDeviceProp prop;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+      const size_t want = M * d * sizeof(float);
+      const size_t carve = want < static_cast<size_t>(prop.persistingL2CacheMaxSize) ? want : static_cast<size_t>(prop.persistingL2CacheMaxSize);
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+      cudaStreamAttrValue attr;
+      memset(&attr, 0, sizeof(attr));
+      attr.accessPolicyWindow.base_ptr = e->h32;
+      attr.accessPolicyWindow.num_bytes = want < static_cast<size_t>(prop.accessPolicyMaxWindowSize) ? want : static_cast<size_t>(prop.accessPolicyMaxWindowSize);
+      attr.accessPolicyWindow.hitRatio = want <= carve ? 1.0f : static_cast<float>(carve) / static_cast<float>(want);
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(e->work, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaGetLastError();
+    }
+  }
   TRY(make_map(&e->m_xin, e->xin16, MB, 3 * e->Kp_in, 3 * e->Kp_in, GEMM_BLOCK_M));
   TRY(make_map(&e->m_h16, e->h16, M, d, d, GEMM_BLOCK_M));
   TRY(make_map(&e->m_att, e->att16, M, d, d, GEMM_BLOCK_M));

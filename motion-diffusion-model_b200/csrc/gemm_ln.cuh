@@ -19,6 +19,7 @@
 #pragma once
 #include "epilogues.cuh"
 #include "gemm.cuh"
+#include "gemm2.cuh"   // g_gemm2_trace (debug stamps)
 
 namespace b200 {
 
@@ -191,8 +192,12 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
         load_resid(rseq, 0);
         load_resid(rseq + 1, 1);
       }
+      long long* tr = (g_gemm2_trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && it >= 1 && it < 3) ? g_gemm2_trace + (it - 1) * 16 : nullptr;
+      int tri = 0;
+      if (tr) tr[tri++] = clock64();
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
+      if (tr) tr[tri++] = clock64();
       float sum = 0.f, sumsq = 0.f;
       if (live) {
         // ---- pass 1
@@ -222,6 +227,7 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
           __syncwarp();
           if (c + 2 < 4) load_resid(rseq + 2, c + 2);
           ++rseq;
+          if (tr) tr[tri++] = clock64();
         }
         tmem_st_wait();
       }
@@ -240,6 +246,7 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
       const float mean = ((p0.x + p1.x) + pr.x) * (1.f / GLN_D);
       const float var = fmaxf(((p0.y + p1.y) + pr.y) * (1.f / GLN_D) - mean * mean, 0.f);
       const float rstd = rsqrtf(var + lp.eps);
+      if (tr) tr[tri++] = clock64();
       if (live) {
         // ---- pass 2
         if (lane == 0) bulk_wait_group_read<0>();
@@ -279,6 +286,7 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
             tma_store_2d(&map_h32, o32, gcol + 32 * c, row0);
             bulk_commit_group();
           }
+          if (tr) tr[tri++] = clock64();
         }
       }
       tc_fence_before();

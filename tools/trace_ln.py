@@ -5,22 +5,23 @@ from b200mdm import _lib
 lib = _lib.load()
 M = 128 * 197
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-buf = torch.zeros(32, dtype=torch.int64, device="cuda")
+buf = torch.zeros(256, dtype=torch.int64, device="cuda")
 lib.b200mdm_debug_trace.argtypes = [ctypes.c_void_p]
-for K, impl in ((512, 0), (1024, 0), (512, 1), (1024, 1)):
+for K in (512, 1024):
     a = torch.randn(M, K, device="cuda").half(); w = (torch.randn(512, K, device="cuda") / K ** 0.5).half()
     b = torch.randn(512, device="cuda"); g = torch.ones(512, device="cuda"); be = torch.zeros(512, device="cuda")
     h32 = torch.randn(M, 512, device="cuda"); h16 = torch.empty(M, 512, device="cuda", dtype=torch.float16)
-    call = lambda: _lib.check(lib.b200mdm_test_gemm_resid_ln(a.data_ptr(), w.data_ptr(), b.data_ptr(), g.data_ptr(), be.data_ptr(), h32.data_ptr(), h16.data_ptr(), M, K, impl, st))
+    call = lambda: _lib.check(lib.b200mdm_test_gemm_resid_ln(a.data_ptr(), w.data_ptr(), b.data_ptr(), g.data_ptr(), be.data_ptr(), h32.data_ptr(), h16.data_ptr(), M, K, 0, st))
     for _ in range(3): call()
     torch.cuda.synchronize()
-    lib.b200mdm_debug_trace(buf.data_ptr()); call(); torch.cuda.synchronize(); lib.b200mdm_debug_trace(None)
+    buf.zero_(); lib.b200mdm_debug_trace(buf.data_ptr()); call(); torch.cuda.synchronize(); lib.b200mdm_debug_trace(None)
     t = buf.cpu().tolist()
     for it in range(2):
-        r = t[it*8:it*8+5]
-        print("K=%d tile %d: wait_acc %d  pass1 %d  stats %d  pass2 %d   (cycles); start offset %d" % (K, it, r[1]-r[0], r[2]-r[1], r[3]-r[2], r[4]-r[3], r[0]-t[0]))
+        r = t[it*16:it*16+11]
+        print("K=%d tile %d: acc_full wait %d | pass1 chunks %s | exchange %d | pass2 chunks %s" % (K, it + 1, r[1]-r[0],
+              [r[i+1]-r[i] for i in range(1, 5)], r[6]-r[5], [r[i+1]-r[i] for i in range(6, 10)]))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10): call()
     e1.record(); torch.cuda.synchronize()
-    print("K=%d impl=%d: %.1f us per launch" % (K, impl, e0.elapsed_time(e1) * 100))
+    print("K=%d: %.1f us per launch" % (K, e0.elapsed_time(e1) * 100))
