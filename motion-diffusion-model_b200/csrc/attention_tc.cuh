@@ -1,35 +1,37 @@
-// Self-attention core on the 5th-generation tensor cores: one CTA per (sample, head), two 128-row query tiles.
+// Self-attention core on the 5th-generation tensor cores: one CTA per (sample, head, 128-row query tile), two CTAs
+// resident per SM so that one CTA's loads / softmax overlap the other's MMAs.
 //   S = Q K^T        tcgen05.mma SS   (Q, K: K-major 128B-swizzled shared-memory tiles brought by TMA)
 //   P = softmax(S)   single pass over all keys (<= 256): fp32 in registers, scale folded into exp2, prefix key mask;
 //                    P is written back to TMEM as packed fp16 *over* the S columns it came from (tcgen05.st)
 //   O = P V          tcgen05.mma TS   (A = P from TMEM, B = V as an MN-major shared-memory operand: V is [key, dh]
-//                    with dh contiguous, exactly what the QKV projection wrote -- no transpose anywhere)
+//                    with dh contiguous, exactly what the QKV projection wrote -- no transpose anywhere).  V is loaded
+//                    into the shared memory K occupied, as soon as QK^T has consumed K: its latency hides behind the
+//                    softmax, and the CTA needs only 32 KB (Q) + 128 B x keys x 2 (K, then V) of shared memory.
 //   O / rowsum -> fp16 -> swizzled slabs (re-using the dead Q tile) -> TMA store
 // (reference: nn.MultiheadAttention inside nn.TransformerEncoderLayer, built at model/mdm.py:77-84; the
 //  key_padding_mask of model/mdm.py:241-247 is a prefix mask => per-sample valid-key count `kvlen`.)
 //
-// Warp roles (320 threads): warp 0 TMA loader, warp 1 TMEM allocator + MMA issuer, warps 2-5 softmax/epilogue of
-// query tile 0, warps 6-9 of query tile 1 (warp w owns TMEM lanes 32*(w%4)..+31; thread = query row).
-// TMEM (512 columns): tile i uses columns [256 i, 256 i + 256):  S at +0..+keys, P (fp16 pairs) at +0..+keys/2,
-// O at +128..+256 (written only after the softmax has consumed S).
-// While tile 0 is in its softmax, the tensor core runs QK^T of tile 1; PV of tile 0 overlaps the softmax of tile 1.
+// Warp roles (192 threads): warp 0 TMA loader, warp 1 TMEM allocator + MMA issuer, warps 2-5 softmax / output
+// (warp w owns TMEM lanes 32*(w%4)..+31; thread = query row).
+// TMEM (256 columns per CTA): S at +0..+keys, P (fp16 pairs) at +0..+keys/2, O at +128..+256 (written only after
+// the softmax has consumed S).
 #pragma once
 #include <cuda_fp16.h>
 
 #include "epilogues.cuh"
+#include "gemm2.cuh"   // g_gemm2_trace (debug stamps)
 #include "ptx.cuh"
 
 namespace b200 {
 
-constexpr int ATC_THREADS = 320;
+constexpr int ATC_THREADS = 192;
 constexpr int ATC_DH = 128;
 constexpr int ATC_MAX_KEYS = 256;
 
 struct AttnTcSmem {
-  // all regions are multiples of 1024 bytes (128B-swizzle atoms); key-dependent sizes are computed at run time
-  static __host__ __device__ constexpr int q_bytes() { return 2 * 2 * 128 * 128; }  // 2 tiles x 2 dh-atoms x [128 x 128 B]
-  static __host__ __device__ int kv_atom_bytes(int keys) { return keys * 128; }       // one dh-atom of K or V
-  static __host__ __device__ int total(int keys) { return 1024 + q_bytes() + 4 * kv_atom_bytes(keys) + 256; }
+  static __host__ __device__ constexpr int q_bytes() { return 2 * 128 * 128; }    // 2 dh-atoms x [128 rows x 128 B]
+  static __host__ __device__ int kv_atom_bytes(int keys) { return keys * 128; }   // one dh-atom of K (later V)
+  static __host__ __device__ int total(int keys) { return 1024 + q_bytes() + 2 * kv_atom_bytes(keys) + 128; }
 };
 
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -46,47 +48,43 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)
                : "memory");
 }
 
-// map_q : qkv16 viewed [n_samples][S][3d], box {64, 128, 1}        (Q tiles)
+// map_q : qkv16 viewed [n_samples][S][3d], box {64, 128, 1}        (Q tile)
 // map_kv: same view, box {64, keys, 1}                              (K / V atoms; keys = round_up(S, 16) <= 256)
 // map_o : att16 viewed [n_samples][S][d], box {64, 32, 1}            (per-warp output slabs)
-__global__ void __launch_bounds__(ATC_THREADS, 1)
+// grid = (heads, n_samples, ceil(S / 128))
+__global__ void __launch_bounds__(ATC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                     const __grid_constant__ CUtensorMap map_o, const int* __restrict__ kvlen, int S, int d, int keys,
                     float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kv_atom = keys * 128;
-  uint8_t* sQ = smem;                         // [tile][atom][128 x 128 B]
-  uint8_t* sK = sQ + AttnTcSmem::q_bytes();   // [atom][keys x 128 B]
-  uint8_t* sV = sK + 2 * kv_atom;             // [atom][keys x 128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * kv_atom);
-  uint64_t* bar_qk = bars;        // [2]  Q tile i (+ K for i = 0) landed
-  uint64_t* bar_v = bars + 2;     //      V landed
-  uint64_t* bar_s = bars + 3;     // [2]  S_i = Q_i K^T complete
-  uint64_t* bar_p = bars + 5;     // [2]  P_i written to TMEM (4 warp arrivals)
-  uint64_t* bar_o = bars + 7;     // [2]  O_i = P_i V complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint8_t* sQ = smem;                         // [atom][128 x 128 B]; later the output slabs
+  uint8_t* sKV = sQ + AttnTcSmem::q_bytes();  // [atom][keys x 128 B]: K, then V
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + 2 * kv_atom);
+  uint64_t* bar_qk = bars;        // Q + K landed
+  uint64_t* bar_v = bars + 1;     // V landed (in K's place)
+  uint64_t* bar_s = bars + 2;     // S = Q K^T complete (K and Q are dead)
+  uint64_t* bar_p = bars + 3;     // P written to TMEM (4 warp arrivals)
+  uint64_t* bar_o = bars + 4;     // O = P V complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x, smp = blockIdx.y;
-  const int n_tiles = (S > 128) ? 2 : 1;
+  const int h = blockIdx.x, smp = blockIdx.y, tile = blockIdx.z;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_kv);
     tma_prefetch_desc(&map_o);
-    mbar_init(&bar_qk[0], 1);
-    mbar_init(&bar_qk[1], 1);
+    mbar_init(bar_qk, 1);
     mbar_init(bar_v, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_s[i], 1);
-      mbar_init(&bar_p[i], 4);
-      mbar_init(&bar_o[i], 1);
-    }
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 4);
+    mbar_init(bar_o, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -98,156 +96,189 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     // ------------------------------------------------------------------ TMA loader
     if (elect_one()) {
       const int cq = h * ATC_DH, ck = d + h * ATC_DH, cv = 2 * d + h * ATC_DH;
-      mbar_expect_tx(&bar_qk[0], 2 * 128 * 128 + 2 * kv_atom);
-      for (int a = 0; a < 2; ++a) tma_load_3d(sQ + a * 16384, &map_q, &bar_qk[0], cq + 64 * a, 0, smp);
-      for (int a = 0; a < 2; ++a) tma_load_3d(sK + a * kv_atom, &map_kv, &bar_qk[0], ck + 64 * a, 0, smp);
-      if (n_tiles == 2) {
-        mbar_expect_tx(&bar_qk[1], 2 * 128 * 128);
-        for (int a = 0; a < 2; ++a) tma_load_3d(sQ + 32768 + a * 16384, &map_q, &bar_qk[1], cq + 64 * a, 128, smp);
-      }
+      mbar_expect_tx(bar_qk, 2 * 128 * 128 + 2 * kv_atom);
+      for (int a = 0; a < 2; ++a) tma_load_3d(sQ + a * 16384, &map_q, bar_qk, cq + 64 * a, tile * 128, smp);
+      for (int a = 0; a < 2; ++a) tma_load_3d(sKV + a * kv_atom, &map_kv, bar_qk, ck + 64 * a, 0, smp);
+      // V replaces K as soon as the tensor core has finished reading K
+      mbar_wait(bar_s, 0);
       mbar_expect_tx(bar_v, 2 * kv_atom);
-      for (int a = 0; a < 2; ++a) tma_load_3d(sV + a * kv_atom, &map_kv, bar_v, cv + 64 * a, 0, smp);
+      for (int a = 0; a < 2; ++a) tma_load_3d(sKV + a * kv_atom, &map_kv, bar_v, cv + 64 * a, 0, smp);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       const uint32_t idesc_s = umma_idesc_f16(128, keys);
       const uint32_t idesc_o = umma_idesc_f16(128, ATC_DH, 0, 1);  // B (= V) is MN-major
-      // S_i = Q_i K^T for both tiles back to back
-      for (int i = 0; i < n_tiles; ++i) {
-        mbar_wait(&bar_qk[i], 0);
-        if (i == 1) mbar_wait(&bar_qk[0], 0);
-        tc_fence_after();
-        const uint32_t tS = tmem_base + i * 256;
+      mbar_wait(bar_qk, 0);
+      tc_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t da = umma_desc_k_sw128(smem_u32(sQ + i * 32768 + (ks >> 2) * 16384) + (ks & 3) * 32);
-          const uint64_t db = umma_desc_k_sw128(smem_u32(sK + (ks >> 2) * kv_atom) + (ks & 3) * 32);
-          umma_f16_ss(tS, da, db, idesc_s, ks != 0);
-        }
-        umma_commit(&bar_s[i]);
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t da = umma_desc_k_sw128(smem_u32(sQ + (ks >> 2) * 16384) + (ks & 3) * 32);
+        const uint64_t db = umma_desc_k_sw128(smem_u32(sKV + (ks >> 2) * kv_atom) + (ks & 3) * 32);
+        umma_f16_ss(tmem_base, da, db, idesc_s, ks != 0);
       }
-      // O_i = P_i V
+      umma_commit(bar_s);
+      // O = P V
       mbar_wait(bar_v, 0);
-      for (int i = 0; i < n_tiles; ++i) {
-        mbar_wait(&bar_p[i], 0);
-        tc_fence_after();
-        const uint32_t tP = tmem_base + i * 256;
-        const uint32_t tO = tmem_base + i * 256 + 128;
-        const int nk = keys >> 4;
-        for (int kk = 0; kk < nk; ++kk) {
-          // V operand: N (= dh) spans the two 64-wide atoms (LBO = atom size), K (= keys) advances 16 rows = 2048 B
-          const uint64_t db = umma_desc_mn_sw128(smem_u32(sV) + kk * 2048, kv_atom, 1024);
-          umma_f16_ts(tO, tP + kk * 8, db, idesc_o, kk != 0);
-        }
-        umma_commit(&bar_o[i]);
+      mbar_wait(bar_p, 0);
+      tc_fence_after();
+      const int nk = keys >> 4;
+      for (int kk = 0; kk < nk; ++kk) {
+        // V operand: N (= dh) spans the two 64-wide atoms (LBO = atom size), K (= keys) advances 16 rows = 2048 B
+        const uint64_t db = umma_desc_mn_sw128(smem_u32(sKV) + kk * 2048, kv_atom, 1024);
+        umma_f16_ts(tmem_base + 128, tmem_base + kk * 8, db, idesc_o, kk != 0);
       }
+      umma_commit(bar_o);
     }
   } else {
     // ------------------------------------------------------------------ softmax + output warps
-    const int tile = (warp - 2) >> 2;   // 0 or 1
     const int q = warp & 3;             // TMEM lane quarter
-    if (tile < n_tiles) {
-      const int kvl = min(kvlen[smp], S);
-      const uint32_t tS = tmem_base + tile * 256 + (static_cast<uint32_t>(q * 32) << 16);
-      const uint32_t tO = tS + 128;
-      mbar_wait(&bar_s[tile], 0);
-      tc_fence_after();
-      const int n32 = keys >> 5, tail16 = keys & 16;
-      // ---- pass 1: row maximum over the valid keys
-      float mx = -INFINITY;
-      for (int c = 0; c < n32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tS + 32 * c, r);
-        tmem_ld_wait();
+    long long* tr = (g_gemm2_trace != nullptr && blockIdx.x == 1 && blockIdx.y == 37 && blockIdx.z == 0 && warp == 2 && lane == 0) ? g_gemm2_trace : nullptr;
+    if (tr) tr[0] = clock64();
+    const int kvl = min(kvlen[smp], S);
+    const uint32_t tS = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t tO = tS + 128;
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    if (tr) tr[1] = clock64();
+    const int n32 = keys >> 5, tail16 = keys & 16;
+    // ---- pass 1: row maximum over the valid keys (next chunk's tcgen05.ld in flight while this one is reduced)
+    float mx = -INFINITY;
+    {
+      uint32_t ra[32], rb[32];
+      uint32_t rt[16];
+      auto max32 = [&](const uint32_t (&r)[32], int c) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (32 * c + j < kvl) mx = fmaxf(mx, __uint_as_float(r[j]));
+      };
+      if (n32 > 0) tmem_ld_32x32(tS, ra);
+#pragma unroll 1
+      for (int c = 0; c < n32; c += 2) {
+        tmem_ld_wait();
+        if (c + 1 < n32) tmem_ld_32x32(tS + 32 * (c + 1), rb);
+        else if (tail16) tmem_ld_32x16(tS + 32 * n32, rt);
+        max32(ra, c);
+        if (c + 1 < n32) {
+          tmem_ld_wait();
+          if (c + 2 < n32) tmem_ld_32x32(tS + 32 * (c + 2), ra);
+          else if (tail16) tmem_ld_32x16(tS + 32 * n32, rt);
+          max32(rb, c + 1);
+        }
       }
       if (tail16) {
-        uint32_t r[16];
-        tmem_ld_32x16(tS + 32 * n32, r);
+        if (n32 == 0) tmem_ld_32x16(tS, rt);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (32 * n32 + j < kvl) mx = fmaxf(mx, __uint_as_float(r[j]));
+          if (32 * n32 + j < kvl) mx = fmaxf(mx, __uint_as_float(rt[j]));
       }
-      const float off = (mx == -INFINITY) ? 0.f : mx * scale_log2;
-      // ---- pass 2: p = exp2(s*scale - max*scale); P (fp16 pairs) overwrites the S columns it trails
-      float sum = 0.f;
-      for (int c = 0; c < n32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tS + 32 * c, r);
-        tmem_ld_wait();
-        uint32_t pk[16];
+    }
+    const float off = (mx == -INFINITY) ? 0.f : mx * scale_log2;
+    if (tr) tr[2] = clock64();
+    // ---- pass 2: p = exp2(s*scale - max*scale); P (fp16 pairs) overwrites the S columns it trails.  The load of
+    // chunk c+1 is issued BEFORE the store of chunk c (register double buffer): a tcgen05.ld queued behind a
+    // tcgen05.st of the same thread otherwise waits for the store (measured: 1600 cycles per chunk vs 290 in pass 1).
+    float sum = 0.f;
+    auto ex2 = [](float x) {
+      float y;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+      return y;
+    };
+    auto softmax32 = [&](uint32_t (&r)[32], int c) {
+      uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float p0 = (32 * c + j < kvl) ? exp2f(fmaf(__uint_as_float(r[j]), scale_log2, -off)) : 0.f;
-          float p1 = (32 * c + j + 1 < kvl) ? exp2f(fmaf(__uint_as_float(r[j + 1]), scale_log2, -off)) : 0.f;
-          sum += p0 + p1;
-          pk[j >> 1] = pack_half2(p0, p1);
+      for (int j = 0; j < 32; j += 2) {
+        const float e0 = ex2(fmaf(__uint_as_float(r[j]), scale_log2, -off));
+        const float e1 = ex2(fmaf(__uint_as_float(r[j + 1]), scale_log2, -off));
+        const float p0 = (32 * c + j < kvl) ? e0 : 0.f;
+        const float p1 = (32 * c + j + 1 < kvl) ? e1 : 0.f;
+        sum += p0 + p1;
+        pk[j >> 1] = pack_half2(p0, p1);
+      }
+      tmem_st_32x16(tS + 16 * c, pk);
+    };
+    {
+      uint32_t ra[32], rb[32];
+      uint32_t rt[16];
+      if (n32 > 0) tmem_ld_32x32(tS, ra);
+#pragma unroll 1
+      for (int c = 0; c < n32; c += 2) {
+        tmem_ld_wait();
+        if (c + 1 < n32) tmem_ld_32x32(tS + 32 * (c + 1), rb);
+        else if (tail16) tmem_ld_32x16(tS + 32 * n32, rt);
+        softmax32(ra, c);
+        if (c + 1 < n32) {
+          tmem_ld_wait();
+          if (c + 2 < n32) tmem_ld_32x32(tS + 32 * (c + 2), ra);
+          else if (tail16) tmem_ld_32x16(tS + 32 * n32, rt);
+          softmax32(rb, c + 1);
         }
-        tmem_st_32x16(tS + 16 * c, pk);
       }
       if (tail16) {
-        uint32_t r[16];
-        tmem_ld_32x16(tS + 32 * n32, r);
+        if (n32 == 0) tmem_ld_32x16(tS, rt);
         tmem_ld_wait();
         uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
-          float p0 = (32 * n32 + j < kvl) ? exp2f(fmaf(__uint_as_float(r[j]), scale_log2, -off)) : 0.f;
-          float p1 = (32 * n32 + j + 1 < kvl) ? exp2f(fmaf(__uint_as_float(r[j + 1]), scale_log2, -off)) : 0.f;
+          const float e0 = ex2(fmaf(__uint_as_float(rt[j]), scale_log2, -off));
+          const float e1 = ex2(fmaf(__uint_as_float(rt[j + 1]), scale_log2, -off));
+          const float p0 = (32 * n32 + j < kvl) ? e0 : 0.f;
+          const float p1 = (32 * n32 + j + 1 < kvl) ? e1 : 0.f;
           sum += p0 + p1;
           pk[j >> 1] = pack_half2(p0, p1);
         }
         tmem_st_32x8(tS + 16 * n32, pk);
       }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_p[tile]);
-      // ---- O / rowsum -> fp16 slabs (the Q tile is dead once bar_s fired) -> TMA store
-      const float inv = sum > 0.f ? 1.f / sum : 0.f;
-      mbar_wait(&bar_o[tile], 0);
-      tc_fence_after();
-      uint8_t* slab0 = sQ + tile * 32768 + q * 4096;   // rows [32q, 32q+32) of dh-atom 0
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tO + 32 * c, r);
-        tmem_ld_wait();
-        uint8_t* slab = slab0 + (c >> 1) * 16384;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 v4;
-          v4.x = pack_half2(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
-          v4.y = pack_half2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
-          v4.z = pack_half2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
-          v4.w = pack_half2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
-          *reinterpret_cast<uint4*>(slab + slab_off(lane, (c & 1) * 4 + j)) = v4;
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        const int row0 = tile * 128 + q * 32;
-        if (row0 < S) {
-          tma_store_3d(&map_o, slab0, h * ATC_DH, row0, smp);
-          tma_store_3d(&map_o, slab0 + 16384, h * ATC_DH + 64, row0, smp);
-          bulk_commit_group();
-          bulk_wait_group<0>();
-        }
-      }
-      __syncwarp();
     }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_p);
+    if (tr) tr[3] = clock64();
+    // ---- O / rowsum -> fp16 slabs (the Q tile is dead once bar_s fired) -> TMA store
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    if (tr) tr[4] = clock64();
+    uint8_t* slab0 = sQ + q * 4096;   // rows [32q, 32q+32) of dh-atom 0
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      tmem_ld_32x32(tO + 32 * c, r);
+      tmem_ld_wait();
+      uint8_t* slab = slab0 + (c >> 1) * 16384;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 v4;
+        v4.x = pack_half2(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+        v4.y = pack_half2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+        v4.z = pack_half2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+        v4.w = pack_half2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+        *reinterpret_cast<uint4*>(slab + slab_off(lane, (c & 1) * 4 + j)) = v4;
+      }
+    }
+    if (tr) tr[5] = clock64();
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      const int row0 = tile * 128 + q * 32;
+      if (row0 < S) {
+        tma_store_3d(&map_o, slab0, h * ATC_DH, row0, smp);
+        tma_store_3d(&map_o, slab0 + 16384, h * ATC_DH + 64, row0, smp);
+        bulk_commit_group();
+        bulk_wait_group<0>();
+      }
+    }
+    __syncwarp();
+    if (tr) tr[6] = clock64();
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 

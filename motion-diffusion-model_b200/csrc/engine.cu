@@ -286,7 +286,7 @@ static int launch_attention_tc(const AttnMaps& m, const int* kvlen, int n_sample
   if (d != H * ATC_DH) return fail(B200MDM_ENOTIMPL, "attention: head_dim must be 128");
   const int keys = (S + 15) & ~15;
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(ATC_DH));
-  attention_tc_kernel<<<dim3(H, n_samples), ATC_THREADS, AttnTcSmem::total(keys), s>>>(m.q, m.kv, m.o, kvlen, S, d, keys,
+  attention_tc_kernel<<<dim3(H, n_samples, (S + 127) / 128), ATC_THREADS, AttnTcSmem::total(keys), s>>>(m.q, m.kv, m.o, kvlen, S, d, keys,
                                                                                      scale_log2);
   CUDA_TRY(cudaGetLastError());
   return B200MDM_OK;
