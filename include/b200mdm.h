@@ -64,7 +64,8 @@ typedef struct b200mdm_config {
   int32_t mask_frames;       /* args.mask_frames (model/mdm.py:241-247) */
   int32_t pos_embed_max_len; /* args.pos_embed_max_len: rows of the positional table */
   int32_t temb_rows;         /* model timesteps to pre-embed (>= original_num_steps of the diffusion) */
-  int32_t reserved[7];
+  int32_t context_len;       /* trans_dec (DiP) prefix completion: args.context_len frames precede x (model/mdm.py:58-61) */
+  int32_t reserved[6];
 } b200mdm_config;
 
 const char* b200mdm_last_error(void);
@@ -105,6 +106,17 @@ int b200mdm_set_schedule(b200mdm_engine* e, int32_t n_steps, const float* rows_h
 int b200mdm_set_cond(b200mdm_engine* e, int32_t batch, int32_t nframes, const float* cond_embed_dev,
                      const int64_t* lengths_host, const float* scale_dev, int32_t force_uncond,
                      const int64_t* action_host, void* stream);
+
+/* trans_dec (DiP, model/mdm.py:203-206,255-270): conditioning for arch = B200MDM_ARCH_TRANS_DEC.
+ *   enc_text_dev   : y['text_embed'][0], BERT token features [n_tokens, batch, cond_dim] fp32 device (reference layout)
+ *   text_mask_host : y['text_embed'][1], uint8 [batch, n_tokens], 1 = padding (memory_key_padding_mask)
+ *   nframes        : frames of x (pred_len); the sequence is context_len + nframes tokens, no conditioning token
+ * lengths / scale / force_uncond as in b200mdm_set_cond.  Must be followed by b200mdm_set_prefix when context_len > 0. */
+int b200mdm_set_cond_dec(b200mdm_engine* e, int32_t batch, int32_t nframes, const float* enc_text_dev,
+                         const uint8_t* text_mask_host, int32_t n_tokens, const int64_t* lengths_host,
+                         const float* scale_dev, int32_t force_uncond, void* stream);
+/* y['prefix'] [batch, njoints, nfeats, context_len] fp32 device: the frames x is a continuation of. */
+int b200mdm_set_prefix(b200mdm_engine* e, const float* prefix_dev, void* stream);
 
 /* y['inpainting_mask'] (bool as uint8) / y['inpainted_motion'] [B,J,F,T] device pointers
  * (gaussian_diffusion.py:300-304); NULL, NULL clears. */

@@ -10,10 +10,10 @@ Python here is host glue only; the per-step path is hand-written sm_100a CUDA in
 """
 from .utils.model_util import (create_model_and_diffusion, create_gaussian_diffusion, get_model_args,  # noqa: F401
                                load_saved_model, load_model_wo_clip)
-from .utils.sampler_util import ClassifierFreeSampleModel  # noqa: F401
+from .utils.sampler_util import ClassifierFreeSampleModel, AutoRegressiveSampler  # noqa: F401
 from .diffusion.respace import SpacedDiffusion, space_timesteps  # noqa: F401
 from .diffusion.gaussian_diffusion import GaussianDiffusion, get_named_beta_schedule  # noqa: F401
 from .model.mdm import MDM  # noqa: F401
-from .synthetic import synthetic_state_dict, synthetic_inputs  # noqa: F401
+from .synthetic import synthetic_state_dict, synthetic_inputs, synthetic_dip_inputs  # noqa: F401
 
 __version__ = "0.1.0"

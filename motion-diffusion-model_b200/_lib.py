@@ -17,7 +17,8 @@ SCHED_STRIDE = 8
 # every symbol include/b200mdm.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "b200mdm_last_error", "b200mdm_version", "b200mdm_create", "b200mdm_destroy", "b200mdm_load_weight",
-    "b200mdm_finalize_weights", "b200mdm_set_schedule", "b200mdm_set_cond", "b200mdm_set_inpaint",
+    "b200mdm_finalize_weights", "b200mdm_set_schedule", "b200mdm_set_cond", "b200mdm_set_cond_dec", "b200mdm_set_prefix",
+    "b200mdm_set_inpaint",
     "b200mdm_denoise", "b200mdm_sample_step", "b200mdm_sample_loop", "b200mdm_q_sample", "b200mdm_launch_count",
     "b200mdm_test_gemm_f16", "b200mdm_test_attention", "b200mdm_test_gemm_resid_ln", "b200mdm_test_layernorm",
 ]
@@ -26,7 +27,7 @@ SYMBOLS = [
 class Config(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "arch", "latent_dim", "ff_size", "num_layers", "num_heads", "njoints", "nfeats", "cond_mode", "cond_dim",
-        "num_actions", "mask_frames", "pos_embed_max_len", "temb_rows")] + [("reserved", ctypes.c_int32 * 7)]
+        "num_actions", "mask_frames", "pos_embed_max_len", "temb_rows", "context_len")] + [("reserved", ctypes.c_int32 * 6)]
 
 
 class B200MDMError(RuntimeError):
@@ -59,6 +60,8 @@ def load():
     lib.b200mdm_finalize_weights.argtypes = [vp, vp]
     lib.b200mdm_set_schedule.argtypes = [vp, i32, vp, vp]
     lib.b200mdm_set_cond.argtypes = [vp, i32, i32, vp, vp, vp, i32, vp, vp]
+    lib.b200mdm_set_cond_dec.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, i32, vp]
+    lib.b200mdm_set_prefix.argtypes = [vp, vp, vp]
     lib.b200mdm_set_inpaint.argtypes = [vp, vp, vp]
     lib.b200mdm_denoise.argtypes = [vp, vp, vp, vp, vp]
     lib.b200mdm_sample_step.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, vp]

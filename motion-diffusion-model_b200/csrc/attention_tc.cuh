@@ -51,7 +51,9 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)
 // map_q : qkv16 viewed [n_samples][S][3d], box {64, 128, 1}        (Q tile)
 // map_kv: same view, box {64, keys, 1}                              (K / V atoms; keys = round_up(S, 16) <= 256)
 // map_o : att16 viewed [n_samples][S][d], box {64, 32, 1}            (per-warp output slabs)
+//         WIDE: [n_samples][S][2d] = [hi | lo] with hi + lo = O to ~22 bits (trans_dec engine)
 // grid = (heads, n_samples, ceil(S / 128))
+template <bool WIDE>
 __global__ void __launch_bounds__(ATC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                     const __grid_constant__ CUtensorMap map_o, const int* __restrict__ kvlen, int S, int d, int keys,
@@ -243,32 +245,42 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     if (tr) tr[4] = clock64();
     uint8_t* slab0 = sQ + q * 4096;   // rows [32q, 32q+32) of dh-atom 0
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tO + 32 * c, r);
-      tmem_ld_wait();
-      uint8_t* slab = slab0 + (c >> 1) * 16384;
+    for (int part = 0; part < (WIDE ? 2 : 1); ++part) {
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tO + 32 * c, r);
+        tmem_ld_wait();
+        uint8_t* slab = slab0 + (c >> 1) * 16384;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 v4;
-        v4.x = pack_half2(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
-        v4.y = pack_half2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
-        v4.z = pack_half2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
-        v4.w = pack_half2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
-        *reinterpret_cast<uint4*>(slab + slab_off(lane, (c & 1) * 4 + j)) = v4;
+        for (int j = 0; j < 4; ++j) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float x0 = __uint_as_float(r[8 * j + 2 * i]) * inv, x1 = __uint_as_float(r[8 * j + 2 * i + 1]) * inv;
+            w[i] = pack_half2(x0, x1);
+            if (WIDE && part == 1) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+              w[i] = pack_half2(x0 - f.x, x1 - f.y);
+            }
+          }
+          *reinterpret_cast<uint4*>(slab + slab_off(lane, (c & 1) * 4 + j)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
       }
-    }
-    if (tr) tr[5] = clock64();
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      const int row0 = tile * 128 + q * 32;
-      if (row0 < S) {
-        tma_store_3d(&map_o, slab0, h * ATC_DH, row0, smp);
-        tma_store_3d(&map_o, slab0 + 16384, h * ATC_DH + 64, row0, smp);
-        bulk_commit_group();
-        bulk_wait_group<0>();
+      if (tr && part == 0) tr[5] = clock64();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const int row0 = tile * 128 + q * 32;
+        if (row0 < S) {
+          const int colbase = h * ATC_DH + part * d;
+          tma_store_3d(&map_o, slab0, colbase, row0, smp);
+          tma_store_3d(&map_o, slab0 + 16384, colbase + 64, row0, smp);
+          bulk_commit_group();
+          bulk_wait_group<0>();
+        }
       }
+      __syncwarp();
     }
     __syncwarp();
     if (tr) tr[6] = clock64();

@@ -111,6 +111,11 @@ struct LayerW {
   const float *bqkv, *bo, *b1, *b2, *g1, *be1, *g2, *be2;
   CUtensorMap m_wqkv, m_wo, m_w1, m_w2;   // box 128 rows: each CTA of a pair stages half of a 256-row W tile
   CUtensorMap m_wo_256, m_w2_256;         // box 256 rows: residual+LayerNorm kernel (each CTA owns 256 output columns)
+  // trans_dec only: cross-attention (multihead_attn) projections and the third LayerNorm
+  __half *wq_c = nullptr, *wkv_c = nullptr, *wo_c = nullptr;
+  const float *bq_c = nullptr, *bkv_c = nullptr, *bo_c = nullptr, *g3 = nullptr, *be3 = nullptr;
+  CUtensorMap m_wq_c, m_wkv_c, m_wo_c_256;
+  CUtensorMap m_wqkv_hi;   // first K columns only (layer 0 of the wide engine: the embedding GEMM writes no lo half)
 };
 
 struct GraphKey {
@@ -150,6 +155,16 @@ struct b200mdm_engine {
   CUtensorMap m_h32_c, m_h32_u, m_h16_c, m_h16_u;      // per-CFG-half views of h32 / h16 for the embedding epilogue
   float* pe_bias = nullptr;
   bool cond_set = false;
+  // trans_dec (DiP): prefix frames + text-token memory
+  bool dec = false;
+  int ctx = 0, s_off = 1, Mt = 0;
+  int kw = 1;   // 2: fp16 activations between the layer GEMMs are [hi | lo] pairs along K (trans_dec engine)
+  CUtensorMap m_h16_hi;
+  float *encperm = nullptr, *memtok = nullptr, *memproj = nullptr;   // [B*Mt, cond_dim], [B*Mt, d], [Bp*Mt, d]
+  __half *mem16 = nullptr, *qc16 = nullptr, *kvc16 = nullptr;        // [Bp*Mt, d], [M, d], [Bp*Mt, 2d]
+  unsigned char* memmask = nullptr;                                   // [Bp, Mt] 1 = padding
+  CUtensorMap m_mem, m_qc_st, m_kvc_st;
+  bool prefix_set = false;
   const unsigned char* inpaint_mask = nullptr;
   const float* inpaint_motion = nullptr;
   // loop machinery
@@ -196,12 +211,16 @@ static int init_kernel_attrs() {
   TRY((set_gemm2_attr<EpiBiasF16<false>>()));
   TRY((set_gemm2_attr<EpiBiasF16<true>>()));
   TRY((set_gemm2_attr<EpiResidualF32>()));
-  CUDA_TRY(cudaFuncSetAttribute(gemm_resid_ln_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLnSmem::TOTAL));
+  TRY((set_gemm2_attr<EpiBiasF16Wide<true>>()));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_resid_ln_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLnSmem::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_resid_ln_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLnSmem::TOTAL));
   CUDA_TRY(cudaFuncSetAttribute(gemm2_resid_ln_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2LnSmem::TOTAL));
   TRY((set_gemm_attr<128, EpiEmbed>()));
   TRY((set_gemm_attr<96, EpiOutStep>()));
   CUDA_TRY(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                AttnTcSmem::total(ATC_MAX_KEYS)));
+  CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 AttnTcSmem::total(ATC_MAX_KEYS)));
   done = true;
   return B200MDM_OK;
@@ -235,12 +254,15 @@ static int launch_gemm2(const CUtensorMap& a, const CUtensorMap& b, const CUtens
 // distributed shared memory (w256: W map with box 256 rows)
 static int launch_gemm_resid_ln(const CUtensorMap& a, const CUtensorMap& w256, const CUtensorMap& h32_io, __half* h16, int M,
                                 int K, const float* bias, const float* gamma, const float* beta, cudaStream_t s,
-                                int num_sms) {
+                                int num_sms, bool wide = false) {
   const int tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int max_clusters = num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   GemmLnParams lp{bias, gamma, beta, 1e-5f};
-  gemm_resid_ln_cluster<<<2 * clusters, GLN_THREADS, GemmLnSmem::TOTAL, s>>>(a, w256, h32_io, h16, M, K, lp);
+  if (wide)
+    gemm_resid_ln_cluster<true><<<2 * clusters, GLN_THREADS, GemmLnSmem::TOTAL, s>>>(a, w256, h32_io, h16, M, K, lp);
+  else
+    gemm_resid_ln_cluster<false><<<2 * clusters, GLN_THREADS, GemmLnSmem::TOTAL, s>>>(a, w256, h32_io, h16, M, K, lp);
   CUDA_TRY(cudaGetLastError());
   return B200MDM_OK;
 }
@@ -274,20 +296,24 @@ static int launch_attention_mma(const __half* qkv, __half* out, const int* kvlen
 struct AttnMaps {
   CUtensorMap q, kv, o;
 };
-static int make_attn_maps(AttnMaps* m, const __half* qkv, __half* out, int n_samples, int S, int d) {
+static int make_attn_maps(AttnMaps* m, const __half* qkv, __half* out, int n_samples, int S, int d, int kw = 1) {
   const int keys = (S + 15) & ~15;
   TRY(make_map_3d(&m->q, qkv, n_samples, S, 3 * d, 3 * d, 128));
   TRY(make_map_3d(&m->kv, qkv, n_samples, S, 3 * d, 3 * d, keys));
-  TRY(make_map_3d(&m->o, out, n_samples, S, d, d, 32));
+  TRY(make_map_3d(&m->o, out, n_samples, S, kw * d, kw * d, 32));   // kw = 2: [hi | lo] output rows
   return B200MDM_OK;
 }
 // tcgen05 kernel for sequences of up to 256 tokens (every configuration of the reference: 197 / 61 / 60)
-static int launch_attention_tc(const AttnMaps& m, const int* kvlen, int n_samples, int S, int d, int H, cudaStream_t s) {
+static int launch_attention_tc(const AttnMaps& m, const int* kvlen, int n_samples, int S, int d, int H, cudaStream_t s,
+                               bool wide = false) {
   if (d != H * ATC_DH) return fail(B200MDM_ENOTIMPL, "attention: head_dim must be 128");
   const int keys = (S + 15) & ~15;
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(ATC_DH));
-  attention_tc_kernel<<<dim3(H, n_samples, (S + 127) / 128), ATC_THREADS, AttnTcSmem::total(keys), s>>>(m.q, m.kv, m.o, kvlen, S, d, keys,
-                                                                                     scale_log2);
+  const dim3 grid(H, n_samples, (S + 127) / 128);
+  if (wide)
+    attention_tc_kernel<true><<<grid, ATC_THREADS, AttnTcSmem::total(keys), s>>>(m.q, m.kv, m.o, kvlen, S, d, keys, scale_log2);
+  else
+    attention_tc_kernel<false><<<grid, ATC_THREADS, AttnTcSmem::total(keys), s>>>(m.q, m.kv, m.o, kvlen, S, d, keys, scale_log2);
   CUDA_TRY(cudaGetLastError());
   return B200MDM_OK;
 }
@@ -304,8 +330,10 @@ extern "C" int b200mdm_version(void) { return 1; }
 
 extern "C" int b200mdm_create(const b200mdm_config* cfg, b200mdm_engine** out) {
   if (!cfg || !out) return fail(B200MDM_EINVAL, "null argument");
-  if (cfg->arch != B200MDM_ARCH_TRANS_ENC)
-    return fail(B200MDM_ENOTIMPL, "arch %d: only trans_enc is implemented in this revision", cfg->arch);
+  if (cfg->arch != B200MDM_ARCH_TRANS_ENC && cfg->arch != B200MDM_ARCH_TRANS_DEC)
+    return fail(B200MDM_ENOTIMPL, "arch %d: trans_enc and trans_dec are implemented", cfg->arch);
+  if (cfg->arch == B200MDM_ARCH_TRANS_DEC && (cfg->cond_mode != B200MDM_COND_TEXT || cfg->context_len < 0))
+    return fail(B200MDM_ENOTIMPL, "trans_dec needs text-token conditioning (BERT) and context_len >= 0");
   if (cfg->latent_dim != 512 || cfg->num_heads != 4 || cfg->ff_size % 64 || cfg->ff_size <= 0)
     return fail(B200MDM_ENOTIMPL, "kernels are specialised for latent_dim 512 / 4 heads (got %d / %d)", cfg->latent_dim,
                 cfg->num_heads);
@@ -329,6 +357,13 @@ extern "C" int b200mdm_create(const b200mdm_config* cfg, b200mdm_engine** out) {
   e->N_out_pad = ((e->JF + 95) / 96) * 96;
   e->num_sms = prop.multiProcessorCount;
   e->layers.resize(e->L);
+  e->dec = cfg->arch == B200MDM_ARCH_TRANS_DEC;
+  e->ctx = e->dec ? cfg->context_len : 0;
+  e->s_off = e->dec ? e->ctx : 1;
+  // DiP samples with guidance 7.5 (three times the encoder's 2.5): the CFG blend multiplies every activation rounding
+  // error by ~10.  Its fp16 activations are therefore kept as hi + lo pairs; at 60-token sequences the doubled K of
+  // the layer GEMMs is free.
+  e->kw = e->dec ? 2 : 1;
   CUDA_TRY(cudaStreamCreateWithFlags(&e->work, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
@@ -341,6 +376,8 @@ static void free_workspace(b200mdm_engine* e) {
   dfree(e->xin16); dfree(e->h16); dfree(e->qkv16); dfree(e->att16); dfree(e->ffn16); dfree(e->g16);
   dfree(e->h32); dfree(e->tok0); dfree(e->condproj); dfree(e->proj); dfree(e->scale); dfree(e->x_work); dfree(e->pe_bias);
   dfree(e->kvlen); dfree(e->tvec); dfree(e->action);
+  dfree(e->encperm); dfree(e->memtok); dfree(e->memproj); dfree(e->mem16); dfree(e->qc16); dfree(e->kvc16); dfree(e->memmask);
+  e->Mt = 0; e->prefix_set = false;
   e->B = e->T = 0;
   e->cond_set = false;
 }
@@ -356,7 +393,7 @@ extern "C" int b200mdm_destroy(b200mdm_engine* e) {
   drop_graph(e);
   free_workspace(e);
   for (auto& kv : e->store) cudaFree(kv.second.dev);
-  for (auto& l : e->layers) { dfree(l.wqkv); dfree(l.wo); dfree(l.w1); dfree(l.w2); }
+  for (auto& l : e->layers) { dfree(l.wqkv); dfree(l.wo); dfree(l.w1); dfree(l.w2); dfree(l.wq_c); dfree(l.wkv_c); dfree(l.wo_c); }
   dfree(e->w_in3); dfree(e->w_out3); dfree(e->temb_hidden); dfree(e->temb_table); dfree(e->sched); dfree(e->tmap);
   dfree(e->state);
   if (e->work) cudaStreamDestroy(e->work);
@@ -378,8 +415,10 @@ static bool known_weight_name(const b200mdm_engine* e, const std::string& n) {
     if (n == f) return true;
   static const char* per_layer[] = {"self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight",
                                     "self_attn.out_proj.bias", "linear1.weight", "linear1.bias", "linear2.weight",
-                                    "linear2.bias", "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias"};
-  const std::string pre = "seqTransEncoder.layers.";
+                                    "linear2.bias", "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias",
+                                    "multihead_attn.in_proj_weight", "multihead_attn.in_proj_bias",
+                                    "multihead_attn.out_proj.weight", "multihead_attn.out_proj.bias", "norm3.weight", "norm3.bias"};
+  const std::string pre = e->dec ? "seqTransDecoder.layers." : "seqTransEncoder.layers.";
   if (n.compare(0, pre.size(), pre) == 0) {
     size_t dot = n.find('.', pre.size());
     if (dot == std::string::npos) return false;
@@ -431,6 +470,14 @@ static int to_f16(const float* src, __half** dst, size_t n, cudaStream_t s) {
   CUDA_TRY(cudaGetLastError());
   return B200MDM_OK;
 }
+// W [N, K] -> fp16 [N, kw * K]: kw = 2 repeats W along K for activations kept as [hi | lo] (trans_dec engine)
+static int to_f16_k(const float* src, __half** dst, int N, int K, int kw, cudaStream_t s) {
+  if (kw == 1) return to_f16(src, dst, static_cast<size_t>(N) * K, s);
+  TRY(dalloc(dst, static_cast<size_t>(N) * K * 2));
+  f32_to_f16_dup_kernel<<<512, 256, 0, s>>>(src, *dst, N, K);
+  CUDA_TRY(cudaGetLastError());
+  return B200MDM_OK;
+}
 
 extern "C" int b200mdm_finalize_weights(b200mdm_engine* e, void* stream) {
   if (!e) return fail(B200MDM_EINVAL, "null engine");
@@ -456,7 +503,7 @@ extern "C" int b200mdm_finalize_weights(b200mdm_engine* e, void* stream) {
 
   // drop previous repacks
   drop_graph(e);
-  for (auto& l : e->layers) { dfree(l.wqkv); dfree(l.wo); dfree(l.w1); dfree(l.w2); }
+  for (auto& l : e->layers) { dfree(l.wqkv); dfree(l.wo); dfree(l.w1); dfree(l.w2); dfree(l.wq_c); dfree(l.wkv_c); dfree(l.wo_c); }
   dfree(e->w_in3); dfree(e->w_out3); dfree(e->temb_hidden); dfree(e->temb_table);
 
   // split-precision in / out projections: W' = [hi | hi | lo], zero padded
@@ -472,7 +519,7 @@ extern "C" int b200mdm_finalize_weights(b200mdm_engine* e, void* stream) {
 
   for (int l = 0; l < e->L; ++l) {
     LayerW& w = e->layers[l];
-    const std::string p = "seqTransEncoder.layers." + std::to_string(l) + ".";
+    const std::string p = std::string(e->dec ? "seqTransDecoder.layers." : "seqTransEncoder.layers.") + std::to_string(l) + ".";
     const float *wqkv, *wo, *w1, *w2;
     TRY(need(e, p + "self_attn.in_proj_weight", {3 * d, d}, &wqkv));
     TRY(need(e, p + "self_attn.in_proj_bias", {3 * d}, &w.bqkv));
@@ -486,16 +533,36 @@ extern "C" int b200mdm_finalize_weights(b200mdm_engine* e, void* stream) {
     TRY(need(e, p + "norm1.bias", {d}, &w.be1));
     TRY(need(e, p + "norm2.weight", {d}, &w.g2));
     TRY(need(e, p + "norm2.bias", {d}, &w.be2));
-    TRY(to_f16(wqkv, &w.wqkv, static_cast<size_t>(3) * d * d, s));
-    TRY(to_f16(wo, &w.wo, static_cast<size_t>(d) * d, s));
-    TRY(to_f16(w1, &w.w1, static_cast<size_t>(ff) * d, s));
-    TRY(to_f16(w2, &w.w2, static_cast<size_t>(d) * ff, s));
-    TRY(make_map(&w.m_wqkv, w.wqkv, 3 * d, d, d, 128));
-    TRY(make_map(&w.m_wo, w.wo, d, d, d, 128));
-    TRY(make_map(&w.m_w1, w.w1, ff, d, d, 128));
-    TRY(make_map(&w.m_w2, w.w2, d, ff, ff, 128));
-    TRY(make_map(&w.m_wo_256, w.wo, d, d, d, 256));
-    TRY(make_map(&w.m_w2_256, w.w2, d, ff, ff, 256));
+    const int kw = e->kw;   // 2: weights repeated along K for [hi | lo] activations
+    TRY(to_f16_k(wqkv, &w.wqkv, 3 * d, d, kw, s));
+    TRY(to_f16_k(wo, &w.wo, d, d, kw, s));
+    TRY(to_f16_k(w1, &w.w1, ff, d, kw, s));
+    TRY(to_f16_k(w2, &w.w2, d, ff, kw, s));
+    TRY(make_map(&w.m_wqkv, w.wqkv, 3 * d, kw * d, kw * d, 128));
+    TRY(make_map(&w.m_wqkv_hi, w.wqkv, 3 * d, d, kw * d, 128));
+    TRY(make_map(&w.m_wo, w.wo, d, kw * d, kw * d, 128));
+    TRY(make_map(&w.m_w1, w.w1, ff, kw * d, kw * d, 128));
+    TRY(make_map(&w.m_w2, w.w2, d, kw * ff, kw * ff, 128));
+    TRY(make_map(&w.m_wo_256, w.wo, d, kw * d, kw * d, 256));
+    TRY(make_map(&w.m_w2_256, w.w2, d, kw * ff, kw * ff, 256));
+    if (e->dec) {
+      // nn.MultiheadAttention in_proj rows: [Wq; Wk; Wv] -- query from the sequence, key/value from the text memory
+      const float *wc, *bc, *woc;
+      TRY(need(e, p + "multihead_attn.in_proj_weight", {3 * d, d}, &wc));
+      TRY(need(e, p + "multihead_attn.in_proj_bias", {3 * d}, &bc));
+      TRY(need(e, p + "multihead_attn.out_proj.weight", {d, d}, &woc));
+      TRY(need(e, p + "multihead_attn.out_proj.bias", {d}, &w.bo_c));
+      TRY(need(e, p + "norm3.weight", {d}, &w.g3));
+      TRY(need(e, p + "norm3.bias", {d}, &w.be3));
+      w.bq_c = bc;
+      w.bkv_c = bc + d;
+      TRY(to_f16_k(wc, &w.wq_c, d, d, kw, s));
+      TRY(to_f16_k(wc + static_cast<size_t>(d) * d, &w.wkv_c, 2 * d, d, kw, s));
+      TRY(to_f16_k(woc, &w.wo_c, d, d, kw, s));
+      TRY(make_map(&w.m_wq_c, w.wq_c, d, kw * d, kw * d, 128));
+      TRY(make_map(&w.m_wkv_c, w.wkv_c, 2 * d, kw * d, kw * d, 128));
+      TRY(make_map(&w.m_wo_c_256, w.wo_c, d, kw * d, kw * d, 256));
+    }
   }
   // timestep-embedding MLP for every model timestep: temb[t] = W2 silu(W1 pe[t] + b1) + b2
   const int R = e->cfg.temb_rows;
@@ -537,14 +604,15 @@ extern "C" int b200mdm_set_schedule(b200mdm_engine* e, int32_t n_steps, const fl
 static int build_workspace(b200mdm_engine* e, int B, int T, int halves) {
   drop_graph(e);
   free_workspace(e);
-  const int d = e->d, S = T + 1, Bp = halves * B;
+  const int d = e->d, S = T + e->s_off, Bp = halves * B;
   const size_t M = static_cast<size_t>(Bp) * S, MB = static_cast<size_t>(B) * S;
   TRY(dalloc(&e->xin16, MB * 3 * e->Kp_in, true));
-  TRY(dalloc(&e->h16, M * d));
+  const int kw = e->kw;
+  TRY(dalloc(&e->h16, M * d * kw, true));
   TRY(dalloc(&e->h32, M * d));
   TRY(dalloc(&e->qkv16, M * 3 * d));
-  TRY(dalloc(&e->att16, M * d));
-  TRY(dalloc(&e->ffn16, M * e->ff));
+  TRY(dalloc(&e->att16, M * d * kw));
+  TRY(dalloc(&e->ffn16, M * e->ff * kw));
   TRY(dalloc(&e->g16, MB * 3 * d));
   TRY(dalloc(&e->tok0, static_cast<size_t>(Bp) * d));
   TRY(dalloc(&e->condproj, static_cast<size_t>(Bp) * d, true));
@@ -554,6 +622,12 @@ static int build_workspace(b200mdm_engine* e, int B, int T, int halves) {
   TRY(dalloc(&e->kvlen, Bp));
   TRY(dalloc(&e->tvec, B, true));
   TRY(dalloc(&e->action, B, true));
+  if (e->dec) {
+    TRY(dalloc(&e->qc16, M * d));
+    TRY(make_map_t(&e->m_qc_st, e->qc16, 2, M, d, d, 32));
+    e->Mt = 0;              // the text-memory buffers are sized by the packed batch: b200mdm_set_cond_dec rebuilds them
+    e->prefix_set = false;  // xin16 was reallocated
+  }
   e->B = B; e->T = T; e->S = S; e->halves = halves; e->Bp = Bp;
   e->M = static_cast<int>(M); e->MB = static_cast<int>(MB);
   // Keep the fp32 residual stream resident in the L2 (126 MB): it is read and rewritten by every residual+LayerNorm
@@ -578,23 +652,24 @@ static int build_workspace(b200mdm_engine* e, int B, int T, int halves) {
     }
   }
   TRY(make_map(&e->m_xin, e->xin16, MB, 3 * e->Kp_in, 3 * e->Kp_in, GEMM_BLOCK_M));
-  TRY(make_map(&e->m_h16, e->h16, M, d, d, GEMM_BLOCK_M));
-  TRY(make_map(&e->m_att, e->att16, M, d, d, GEMM_BLOCK_M));
-  TRY(make_map(&e->m_ffn, e->ffn16, M, e->ff, e->ff, GEMM_BLOCK_M));
+  TRY(make_map(&e->m_h16, e->h16, M, kw * d, kw * d, GEMM_BLOCK_M));
+  TRY(make_map(&e->m_h16_hi, e->h16, M, d, kw * d, GEMM_BLOCK_M));
+  TRY(make_map(&e->m_att, e->att16, M, kw * d, kw * d, GEMM_BLOCK_M));
+  TRY(make_map(&e->m_ffn, e->ffn16, M, kw * e->ff, kw * e->ff, GEMM_BLOCK_M));
   TRY(make_map(&e->m_g16, e->g16, MB, 3 * d, 3 * d, GEMM_BLOCK_M));
   TRY(make_map_t(&e->m_qkv_st, e->qkv16, 2, M, 3 * d, 3 * d, 32));
-  TRY(make_map_t(&e->m_ffn_st, e->ffn16, 2, M, e->ff, e->ff, 32));
+  TRY(make_map_t(&e->m_ffn_st, e->ffn16, 2, M, kw * e->ff, kw * e->ff, 32));
   TRY(make_map_t(&e->m_h32_io, e->h32, 4, M, d, d, 32));
-  TRY(make_map_t(&e->m_h16_st, e->h16, 2, M, d, d, 32));
+  TRY(make_map_t(&e->m_h16_st, e->h16, 2, M, d, kw * d, 32));
   if (S <= ATC_MAX_KEYS) {
     AttnMaps am;
-    TRY(make_attn_maps(&am, e->qkv16, e->att16, Bp, S, d));
+    TRY(make_attn_maps(&am, e->qkv16, e->att16, Bp, S, d, kw));
     e->m_att_q = am.q; e->m_att_kv = am.kv; e->m_att_o = am.o;
   }
   TRY(make_map_t(&e->m_h32_c, e->h32, 4, MB, d, d, 32));
-  TRY(make_map_t(&e->m_h16_c, e->h16, 2, MB, d, d, 32));
+  TRY(make_map_t(&e->m_h16_c, e->h16, 2, MB, d, kw * d, 32));
   TRY(make_map_t(&e->m_h32_u, e->h32 + (halves == 2 ? MB * d : 0), 4, MB, d, d, 32));
-  TRY(make_map_t(&e->m_h16_u, e->h16 + (halves == 2 ? MB * d : 0), 2, MB, d, d, 32));
+  TRY(make_map_t(&e->m_h16_u, e->h16 + (halves == 2 ? MB * d * kw : 0), 2, MB, d, kw * d, 32));
   TRY(dalloc(&e->pe_bias, static_cast<size_t>(S) * d));
   pe_bias_kernel<<<S, 128>>>(e->pe_bias, e->pe, e->b_in, S, d);
   CUDA_TRY(cudaGetLastError());
@@ -606,6 +681,7 @@ extern "C" int b200mdm_set_cond(b200mdm_engine* e, int32_t batch, int32_t nframe
                                 const int64_t* lengths_host, const float* scale_dev, int32_t force_uncond,
                                 const int64_t* action_host, void* stream) {
   if (!e) return fail(B200MDM_EINVAL, "null engine");
+  if (e->dec) return fail(B200MDM_EINVAL, "trans_dec engines take their conditioning through b200mdm_set_cond_dec");
   if (!e->finalized) return fail(B200MDM_ESTATE, "weights not finalised");
   if (batch <= 0 || nframes <= 0) return fail(B200MDM_EINVAL, "bad batch / nframes");
   if (nframes + 1 > e->cfg.pos_embed_max_len) return fail(B200MDM_EINVAL, "sequence longer than the positional table");
@@ -658,6 +734,82 @@ extern "C" int b200mdm_set_cond(b200mdm_engine* e, int32_t batch, int32_t nframe
   return B200MDM_OK;
 }
 
+// ---- trans_dec (DiP) conditioning: BERT token features + padding mask as the cross-attention memory, prefix frames
+extern "C" int b200mdm_set_cond_dec(b200mdm_engine* e, int32_t batch, int32_t nframes, const float* enc_text_dev,
+                                    const uint8_t* text_mask_host, int32_t n_tokens, const int64_t* lengths_host,
+                                    const float* scale_dev, int32_t force_uncond, void* stream) {
+  if (!e) return fail(B200MDM_EINVAL, "null engine");
+  if (!e->dec) return fail(B200MDM_EINVAL, "b200mdm_set_cond_dec is for trans_dec engines");
+  if (!e->finalized) return fail(B200MDM_ESTATE, "weights not finalised");
+  if (batch <= 0 || nframes <= 0 || n_tokens <= 0 || n_tokens > 64) return fail(B200MDM_EINVAL, "bad batch / nframes / n_tokens (1..64)");
+  if (nframes + e->ctx > e->cfg.pos_embed_max_len) return fail(B200MDM_EINVAL, "sequence longer than the positional table");
+  if (!enc_text_dev || !text_mask_host) return fail(B200MDM_EINVAL, "DiP needs y['text_embed'] = (tokens, mask)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int halves = scale_dev ? 2 : 1;
+  if (batch != e->B || nframes != e->T || halves != e->halves) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    TRY(build_workspace(e, batch, nframes, halves));
+  }
+  const int d = e->d, B = batch, S = e->S, Bp = e->Bp, Mt = n_tokens, C = e->cfg.cond_dim;
+  if (Mt != e->Mt) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    drop_graph(e);
+    dfree(e->encperm); dfree(e->memtok); dfree(e->memproj); dfree(e->mem16); dfree(e->kvc16); dfree(e->memmask);
+    TRY(dalloc(&e->encperm, static_cast<size_t>(B) * Mt * C));
+    TRY(dalloc(&e->memtok, static_cast<size_t>(B) * Mt * d));
+    TRY(dalloc(&e->memproj, static_cast<size_t>(Bp) * Mt * d));
+    TRY(dalloc(&e->mem16, static_cast<size_t>(Bp) * Mt * 2 * d));   // [hi | lo]
+    TRY(dalloc(&e->kvc16, static_cast<size_t>(Bp) * Mt * 2 * d));
+    TRY(dalloc(&e->memmask, static_cast<size_t>(Bp) * Mt));
+    TRY(make_map(&e->m_mem, e->mem16, static_cast<uint64_t>(Bp) * Mt, 2 * d, 2 * d, GEMM_BLOCK_M));
+    TRY(make_map_t(&e->m_kvc_st, e->kvc16, 2, static_cast<uint64_t>(Bp) * Mt, 2 * d, 2 * d, 32));
+    e->Mt = Mt;
+  }
+  // key mask of the frames: the context frames are always valid (model/mdm.py:204-206), then `lengths` frames of x
+  std::vector<int> kv(Bp, S);
+  if (e->cfg.mask_frames && lengths_host && S > 1) {
+    for (int b = 0; b < Bp; ++b) {
+      long long len = lengths_host[b % B];
+      if (len < 0) len = 0;
+      if (len > nframes) len = nframes;
+      kv[b] = static_cast<int>(len) + e->ctx;
+    }
+  }
+  std::vector<unsigned char> mk(static_cast<size_t>(Bp) * Mt);
+  for (int b = 0; b < Bp; ++b)
+    for (int m = 0; m < Mt; ++m) mk[static_cast<size_t>(b) * Mt + m] = text_mask_host[static_cast<size_t>(b % B) * Mt + m] ? 1 : 0;
+  CUDA_TRY(cudaMemcpyAsync(e->kvlen, kv.data(), kv.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(e->memmask, mk.data(), mk.size(), cudaMemcpyHostToDevice, s));
+  if (scale_dev) CUDA_TRY(cudaMemcpyAsync(e->scale, scale_dev, B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  // text_emb = embed_text(mask_cond(enc_text)) per token (model/mdm.py:218), once per loop
+  permute_mbc_kernel<<<dim3(Mt, B), 128, 0, s>>>(enc_text_dev, e->encperm, Mt, B, C);
+  CUDA_TRY(cudaGetLastError());
+  const size_t warps = static_cast<size_t>(B) * Mt * d;
+  small_linear_kernel<0><<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, s>>>(e->encperm, e->w_txt, e->b_txt, e->memtok, B * Mt, d, C, C);
+  CUDA_TRY(cudaGetLastError());
+  memproj_fill_kernel<<<dim3(Mt, Bp), 128, 0, s>>>(e->memproj, e->memtok, e->b_txt, B, Mt, d, Bp, (halves == 1 && force_uncond) ? 1 : 0);
+  CUDA_TRY(cudaGetLastError());
+  e->launches += 3;
+  e->cond_set = true;
+  return B200MDM_OK;
+}
+
+// y['prefix'] [B, J, F, context_len] (model/mdm.py:203-206): packed once per loop into the first context_len rows of
+// every sequence of the embedding GEMM's A operand.
+extern "C" int b200mdm_set_prefix(b200mdm_engine* e, const float* prefix_dev, void* stream) {
+  if (!e || !prefix_dev) return fail(B200MDM_EINVAL, "null argument");
+  if (!e->dec || e->ctx <= 0) return fail(B200MDM_EINVAL, "this engine has no prefix (context_len == 0)");
+  if (!e->cond_set) return fail(B200MDM_ESTATE, "call b200mdm_set_cond_dec first (it sizes the workspace)");
+  dim3 grid((e->ctx + 31) / 32, (e->JF + 31) / 32, e->B), block(32, 8);
+  pack_input_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(prefix_dev, e->xin16, e->B, e->JF, e->ctx, e->S, e->Kp_in,
+                                                                          3 * e->Kp_in, 0);
+  CUDA_TRY(cudaGetLastError());
+  e->launches++;
+  e->prefix_set = true;
+  return B200MDM_OK;
+}
+
 extern "C" int b200mdm_set_inpaint(b200mdm_engine* e, const uint8_t* mask_dev, const float* motion_dev) {
   if (!e) return fail(B200MDM_EINVAL, "null engine");
   if ((mask_dev == nullptr) != (motion_dev == nullptr)) return fail(B200MDM_EINVAL, "inpainting needs both mask and motion");
@@ -684,7 +836,7 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
   int nk = 0;
   {
     dim3 grid((T + 31) / 32, (JF + 31) / 32, B), block(32, 8);
-    pack_input_kernel<<<grid, block, 0, s>>>(a.x_in, e->xin16, B, JF, T, S, Kp, 3 * Kp, 1);
+    pack_input_kernel<<<grid, block, 0, s>>>(a.x_in, e->xin16, B, JF, T, S, Kp, 3 * Kp, e->s_off);
     CUDA_TRY(cudaGetLastError());
     ++nk;
   }
@@ -696,28 +848,60 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
     TRY((launch_gemm<128, EpiEmbed>(e->m_xin, e->m_win, e->m_xin, e->MB, d, 3 * Kp, p, s, e->num_sms)));
     ++nk;
   }
-  tok0_rows_kernel<<<e->Bp, 128, 0, s>>>(e->h32, e->h16, e->condproj, e->temb_table, e->pe,
-                                         a.explicit_t ? e->tvec : nullptr, e->tmap, e->state, B, S, d, e->cfg.temb_rows);
+  if (!e->dec) {
+    tok0_rows_kernel<<<e->Bp, 128, 0, s>>>(e->h32, e->h16, e->condproj, e->temb_table, e->pe,
+                                           a.explicit_t ? e->tvec : nullptr, e->tmap, e->state, B, S, d, e->cfg.temb_rows);
+  } else {
+    // cross-attention memory of this step: text tokens + timestep embedding (model/mdm.py:218-220)
+    mem_build_kernel<<<dim3(e->Mt, e->Bp), 128, 0, s>>>(e->mem16, e->memproj, e->temb_table, a.explicit_t ? e->tvec : nullptr,
+                                                        e->tmap, e->state, B, e->Mt, d, e->cfg.temb_rows);
+  }
   CUDA_TRY(cudaGetLastError());
   ++nk;
+  const int kw = e->kw;
+  const bool wide = kw == 2;
   for (int l = 0; l < e->L; ++l) {
     const LayerW& w = e->layers[l];
     {
+      // wide engine, layer 0: the embedding GEMM leaves only the hi half of h16 -> K = d over the first half of [W | W]
+      const bool hi_only = wide && l == 0;
       EpiBiasF16<false>::Params p{w.bqkv};
-      TRY((launch_gemm2<EpiBiasF16<false>>(e->m_h16, w.m_wqkv, e->m_qkv_st, e->M, 3 * d, d, p, s, e->num_sms)));
+      TRY((launch_gemm2<EpiBiasF16<false>>(hi_only ? e->m_h16_hi : e->m_h16, hi_only ? w.m_wqkv_hi : w.m_wqkv, e->m_qkv_st, e->M,
+                                           3 * d, hi_only ? d : kw * d, p, s, e->num_sms)));
     }
     if (S <= ATC_MAX_KEYS) {
       AttnMaps am{e->m_att_q, e->m_att_kv, e->m_att_o};
-      TRY(launch_attention_tc(am, e->kvlen, e->Bp, S, d, e->H, s));
+      TRY(launch_attention_tc(am, e->kvlen, e->Bp, S, d, e->H, s, wide));
     } else {
+      if (wide) return fail(B200MDM_ENOTIMPL, "trans_dec sequences longer than %d tokens", ATC_MAX_KEYS);
       TRY(launch_attention_mma(e->qkv16, e->att16, e->kvlen, e->Bp, S, d, e->H, s));
     }
-    TRY(launch_gemm_resid_ln(e->m_att, w.m_wo_256, e->m_h32_io, e->h16, e->M, d, w.bo, w.g1, w.be1, s, e->num_sms));
-    {
+    TRY(launch_gemm_resid_ln(e->m_att, w.m_wo_256, e->m_h32_io, e->h16, e->M, kw * d, w.bo, w.g1, w.be1, s, e->num_sms, wide));
+    if (e->dec) {
+      // cross-attention block of nn.TransformerDecoderLayer: q from the sequence, k/v from the text memory
+      {
+        EpiBiasF16<false>::Params p{w.bq_c};
+        TRY((launch_gemm2<EpiBiasF16<false>>(e->m_h16, w.m_wq_c, e->m_qc_st, e->M, d, kw * d, p, s, e->num_sms)));
+      }
+      {
+        EpiBiasF16<false>::Params p{w.bkv_c};
+        TRY((launch_gemm2<EpiBiasF16<false>>(e->m_mem, w.m_wkv_c, e->m_kvc_st, e->Bp * e->Mt, 2 * d, kw * d, p, s, e->num_sms)));
+      }
+      cross_attention_kernel<<<dim3(e->H, e->Bp), 128, static_cast<size_t>(e->Mt) * 512, s>>>(
+          e->qc16, e->kvc16, e->memmask, e->att16, S, e->Mt, d, 1.0f / sqrtf(128.0f));
+      CUDA_TRY(cudaGetLastError());
+      TRY(launch_gemm_resid_ln(e->m_att, w.m_wo_c_256, e->m_h32_io, e->h16, e->M, kw * d, w.bo_c, w.g2, w.be2, s, e->num_sms, wide));
+      nk += 4;
+    }
+    if (wide) {
+      EpiBiasF16Wide<true>::Params p{w.b1, ff};
+      TRY((launch_gemm2<EpiBiasF16Wide<true>>(e->m_h16, w.m_w1, e->m_ffn_st, e->M, ff, kw * d, p, s, e->num_sms)));
+    } else {
       EpiBiasF16<true>::Params p{w.b1};
       TRY((launch_gemm2<EpiBiasF16<true>>(e->m_h16, w.m_w1, e->m_ffn_st, e->M, ff, d, p, s, e->num_sms)));
     }
-    TRY(launch_gemm_resid_ln(e->m_ffn, w.m_w2_256, e->m_h32_io, e->h16, e->M, ff, w.b2, w.g2, w.be2, s, e->num_sms));
+    TRY(launch_gemm_resid_ln(e->m_ffn, w.m_w2_256, e->m_h32_io, e->h16, e->M, kw * ff, w.b2, e->dec ? w.g3 : w.g2,
+                             e->dec ? w.be3 : w.be2, s, e->num_sms, wide));
     nk += 5;
   }
   blend_split_kernel<<<(e->MB + 7) / 8, 256, 0, s>>>(e->h32, e->g16, e->scale, B, S, d, e->halves);
@@ -736,6 +920,7 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
     p.state = e->state;
     p.noise_batch_stride = a.const_noise ? 0 : static_cast<long long>(JF) * T;
     p.B = B; p.S = S; p.T = T; p.J = JF; p.mode = a.mode;
+    p.s_off = e->s_off;
     p.clip_denoised = a.clip;
     TRY((launch_gemm<96, EpiOutStep>(e->m_g16, e->m_wout, e->m_g16, e->MB, e->N_out_pad, 3 * d, p, s, e->num_sms)));
     ++nk;
@@ -748,6 +933,7 @@ static int check_ready(b200mdm_engine* e, bool need_sched) {
   if (!e) return fail(B200MDM_EINVAL, "null engine");
   if (!e->finalized) return fail(B200MDM_ESTATE, "weights not finalised");
   if (!e->cond_set) return fail(B200MDM_ESTATE, "b200mdm_set_cond has not been called");
+  if (e->dec && e->ctx > 0 && !e->prefix_set) return fail(B200MDM_ESTATE, "b200mdm_set_prefix has not been called (y['prefix'])");
   if (need_sched && e->n_steps <= 0) return fail(B200MDM_ESTATE, "b200mdm_set_schedule has not been called");
   return B200MDM_OK;
 }

@@ -127,6 +127,69 @@ struct EpiBiasF16 {
 };
 
 // ---------------------------------------------------------------------------------------------------------
+// EpiBiasF16 with the result kept as a [hi | lo] fp16 pair: out16[row, col] = hi, out16[row, lo_col + col] = lo with
+// hi + lo = act(acc + bias) to ~22 bits (trans_dec engine, where guidance 7.5 amplifies activation rounding; the
+// consumer GEMM runs over K = 2N against [W | W]).  map_c: fp16 [M, 2N], box {64 cols, 32 rows}, SWIZZLE_128B.
+template <bool GELU>
+struct EpiBiasF16Wide {
+  static constexpr int SMEM_PER_WARP = 2 * 4096;   // one hi slab + one lo slab
+  static constexpr bool RELEASE_EARLY = true;
+  struct Params {
+    const float* bias;
+    int lo_col;
+  };
+  static __device__ __forceinline__ void preload(const Params& p, float* dst, int N, int tid, int nthreads) {
+    for (int i = tid; i < N; i += nthreads) dst[i] = p.bias[i];
+  }
+  static __device__ __forceinline__ void tile_begin(EpiCtx&, const Params&, int, int) {}
+  static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0,
+                                               int) {
+    const int half = (col0 >> 5) & 1;
+    uint8_t* slab_hi = ctx.smem;
+    uint8_t* slab_lo = ctx.smem + 4096;
+    if (half == 0) {
+      if (ctx.lane == 0) bulk_wait_group_read<0>();
+      __syncwarp();
+    }
+    const float* bs = ctx.bias_all + col0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float x0 = __uint_as_float(raw[8 * j + 2 * i]) + bs[8 * j + 2 * i];
+        float x1 = __uint_as_float(raw[8 * j + 2 * i + 1]) + bs[8 * j + 2 * i + 1];
+        if (GELU) {
+          x0 = gelu_erf(x0); x1 = gelu_erf(x1);
+        }
+        const __half2 h = __floats2half2_rn(x0, x1);
+        const float2 f = __half22float2(h);
+        const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+      }
+      *reinterpret_cast<uint4*>(slab_hi + slab_off(ctx.lane, half * 4 + j)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(slab_lo + slab_off(ctx.lane, half * 4 + j)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    if (half == 1 || col0 + 32 >= ctx.N) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (ctx.lane == 0) {
+        tma_store_2d(ctx.map_c, slab_hi, col0 - 32 * half, row0);
+        tma_store_2d(ctx.map_c, slab_lo, p.lo_col + col0 - 32 * half, row0);
+        bulk_commit_group();
+      }
+      ctx.seq++;
+    }
+  }
+  static __device__ __forceinline__ void tile_end(EpiCtx&, const Params&, int, int, uint32_t) {}
+  static __device__ __forceinline__ void finish(EpiCtx& ctx) {
+    if (ctx.lane == 0) bulk_wait_group<0>();
+    __syncwarp();
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
 // h32[row, col] += acc + bias[col]      (attention out-projection / FFN down-projection + residual, in place).
 // Per 32-column chunk: TMA load of the residual slab (issued one chunk ahead, three rotating buffers), add in
 // registers, write back into the same slab, TMA store.  map_c: fp32 [M, N], box {32 cols, 32 rows}, SWIZZLE_128B.
@@ -289,6 +352,7 @@ struct EpiOutStep {
     const StepState* state;
     long long noise_batch_stride;  // J*T normally, 0 for const_noise
     int B, S, T, J, mode;
+    int s_off;                // rows s < s_off of a sequence are not frames of x (cond token / DiP prefix); t = s - s_off
     int clip_denoised;        // clamp x0 to [-1, 1] after the inpainting blend (gaussian_diffusion.py:348-352)
   };
   static __device__ __forceinline__ void tile_begin(EpiCtx&, const Params&, int, int) {}
@@ -297,8 +361,8 @@ struct EpiOutStep {
     const int row = row0 + ctx.lane;
     if (row >= ctx.M) return;
     const int b = row / p.S, s = row - b * p.S;
-    if (s == 0) return;
-    const int t = s - 1;
+    if (s < p.s_off) return;
+    const int t = s - p.s_off;
     float c1 = 0.f, c2 = 0.f, sg = 0.f, sr = 0.f, srm1 = 1.f, sq = 0.f, ce = 0.f;
     const float* nz = nullptr;
     if (p.mode != 0) {

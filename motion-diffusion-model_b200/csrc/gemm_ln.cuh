@@ -48,7 +48,9 @@ struct GemmLnParams {
 };
 
 // map_a: A [M, K] fp16, box 128 rows; map_b: W [512, K] fp16, box 256 rows; map_h32: h32 [M, 512] fp32, box 32 x 32
-// (loaded and stored in place); h16 [M, 512] fp16
+// (loaded and stored in place); h16 [M, 512] fp16 -- or, WIDE, [M, 1024] = [hi | lo] (trans_dec engine: the next GEMM
+// runs over K = 1024 against [W | W], which keeps the normalised activations to ~22 bits)
+template <bool WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GLN_THREADS, 1)
 gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ CUtensorMap map_h32, __half* __restrict__ h16, int M, int K,
@@ -262,6 +264,7 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
             __syncwarp();
           }
           uint32_t pk[16];
+          uint32_t pl[WIDE ? 16 : 1];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 g = *reinterpret_cast<const float4*>(gamma_s + 32 * c + 4 * j);
@@ -274,11 +277,21 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
             *reinterpret_cast<float4*>(o32 + slab_off(lane, j)) = y;
             pk[2 * j] = pack_half2(y.x, y.y);
             pk[2 * j + 1] = pack_half2(y.z, y.w);
+            if (WIDE) {
+              const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&pk[2 * j]));
+              const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&pk[2 * j + 1]));
+              pl[2 * j] = pack_half2(y.x - f0.x, y.y - f0.y);
+              pl[2 * j + 1] = pack_half2(y.z - f1.x, y.w - f1.y);
+            }
           }
           if (row0 + lane < M) {   // fp16 copy: 64 contiguous bytes of this thread's row, two whole 32-byte sectors
-            __half* dst = h16 + static_cast<size_t>(row0 + lane) * GLN_D + gcol + 32 * c;
+            __half* dst = h16 + static_cast<size_t>(row0 + lane) * (WIDE ? 2 * GLN_D : GLN_D) + gcol + 32 * c;
             stg256(dst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
             stg256(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+            if (WIDE) {
+              stg256(dst + GLN_D, pl[0], pl[1], pl[2], pl[3], pl[4], pl[5], pl[6], pl[7]);
+              stg256(dst + GLN_D + 16, pl[8], pl[9], pl[10], pl[11], pl[12], pl[13], pl[14], pl[15]);
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();

@@ -159,6 +159,18 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restr
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
     dst[i] = __float2half_rn(src[i]);
 }
+// W [N, K] fp32 -> [W16 | W16] fp16 [N, 2K]: partner of activations stored as [hi | lo] along K (the trans_dec engine keeps
+// its fp16 activations to ~22 mantissa bits this way; the product A_hi W + A_lo W accumulates in fp32 on the tensor core).
+__global__ void f32_to_f16_dup_kernel(const float* __restrict__ src, __half* __restrict__ dst, int N, int K) {
+  const size_t n = static_cast<size_t>(N) * K;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = i / K, k = i % K;
+    const __half h = __float2half_rn(src[i]);
+    dst[r * 2 * K + k] = h;
+    dst[r * 2 * K + K + k] = h;
+  }
+}
 // W [N, K] fp32 -> W' [Npad, 3*Kp] fp16 = [hi | hi | lo] (zero padding), partner of the [hi | lo | hi] activations.
 __global__ void split_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int N, int K, int Kp) {
   const int n = blockIdx.x;
@@ -223,6 +235,107 @@ __global__ void q_sample_kernel(float* __restrict__ out, const float* __restrict
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float s = (x0 != nullptr) ? x0[i] : 0.f;
     out[i] = __fadd_rn(__fmul_rn(a, s), __fmul_rn(b, noise[i]));
+  }
+}
+
+}  // namespace b200
+
+// ===================================================================================================================
+// trans_dec (DiP) helpers -- reference model/mdm.py:255-270 and torch nn.TransformerDecoderLayer cross-attention
+namespace b200 {
+
+// mem16[b', m, :] = [hi | lo] fp16 of ( memproj[b', m, :] + temb_table[t(b'), :] )   (emb = text_emb + time_emb,
+// mdm.py:218-220; the time embedding is broadcast over the text tokens).  Rows are 2d wide.  grid = (Mt, Bp)
+__global__ void mem_build_kernel(__half* __restrict__ mem16, const float* __restrict__ memproj,
+                                 const float* __restrict__ temb_table, const int* __restrict__ tvec,
+                                 const int* __restrict__ tmap, const StepState* __restrict__ state, int B, int Mt, int d,
+                                 int temb_rows) {
+  const int m = blockIdx.x, bp = blockIdx.y;
+  int t = (tvec != nullptr) ? tvec[bp % B] : tmap[state->cur];
+  t = min(max(t, 0), temb_rows - 1);
+  const size_t row = static_cast<size_t>(bp) * Mt + m;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const float v = memproj[row * d + c] + temb_table[static_cast<size_t>(t) * d + c];
+    const __half hi = __float2half_rn(v);
+    mem16[row * 2 * d + c] = hi;
+    mem16[row * 2 * d + d + c] = __float2half_rn(v - __half2float(hi));
+  }
+}
+
+// memproj rows of the packed batch: cond half = W enc + b (already in proj [B*Mt, d], row (b, m)), uncond half = b.
+__global__ void memproj_fill_kernel(float* __restrict__ memproj, const float* __restrict__ proj,
+                                    const float* __restrict__ bias, int B, int Mt, int d, int rows_bp, int first_uncond) {
+  const int m = blockIdx.x, bp = blockIdx.y;
+  if (bp >= rows_bp) return;
+  const bool unc = first_uncond ? true : (bp >= B);
+  const int b = bp % B;
+  for (int c = threadIdx.x; c < d; c += blockDim.x)
+    memproj[(static_cast<size_t>(bp) * Mt + m) * d + c] = unc ? bias[c] : proj[(static_cast<size_t>(b) * Mt + m) * d + c];
+}
+
+// enc_text [Mt, B, C] (reference layout, model/mdm.py:185) -> [B*Mt, C] rows (b, m) so that one small GEMM projects it
+__global__ void permute_mbc_kernel(const float* __restrict__ src, float* __restrict__ dst, int Mt, int B, int C) {
+  const int m = blockIdx.x, b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    dst[(static_cast<size_t>(b) * Mt + m) * C + c] = src[(static_cast<size_t>(m) * B + b) * C + c];
+}
+
+// Cross-attention core: softmax(q k^T / sqrt(128) + mask) v with a handful of memory tokens (Mt <= 64).
+//   q16 [n_samples*S, d] (head h at columns h*128), kv16 [n_samples*Mt, 2d] (k | v), mask [n_samples, Mt] (1 = ignore),
+//   out16 [n_samples*S, 2d] = [hi | lo].  One warp per query row, lane owns 4 of the 128 head dimensions.  ~0.5 GFLOP per layer at the
+//   DiP configuration (60 x 16 tokens): CUDA cores are enough, the projections around it run on the tensor cores.
+// grid = (heads, n_samples), block = 128
+__global__ void cross_attention_kernel(const __half* __restrict__ q16, const __half* __restrict__ kv16,
+                                       const unsigned char* __restrict__ mask, __half* __restrict__ out16, int S, int Mt,
+                                       int d, float scale) {
+  extern __shared__ __half ca_smem[];   // [2][Mt][128]
+  const int h = blockIdx.x, smp = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  __half* sK = ca_smem;
+  __half* sV = ca_smem + Mt * 128;
+  for (int i = threadIdx.x; i < Mt * 16; i += blockDim.x) {   // 16-byte chunks
+    const int m = i >> 4, ch = i & 15;
+    const __half* src = kv16 + (static_cast<size_t>(smp) * Mt + m) * 2 * d + h * 128 + ch * 8;
+    *reinterpret_cast<uint4*>(sK + m * 128 + ch * 8) = *reinterpret_cast<const uint4*>(src);
+    *reinterpret_cast<uint4*>(sV + m * 128 + ch * 8) = *reinterpret_cast<const uint4*>(src + d);
+  }
+  __syncthreads();
+  const unsigned char* mk = mask + static_cast<size_t>(smp) * Mt;
+  for (int s = warp; s < S; s += nwarp) {
+    const size_t row = static_cast<size_t>(smp) * S + s;
+    const __half2* qp = reinterpret_cast<const __half2*>(q16 + row * d + h * 128 + lane * 4);
+    const float2 qa = __half22float2(qp[0]), qb = __half22float2(qp[1]);
+    float sc[64];
+    float mx = -INFINITY;
+#pragma unroll 4
+    for (int m = 0; m < Mt; ++m) {
+      const __half2* kp = reinterpret_cast<const __half2*>(sK + m * 128 + lane * 4);
+      const float2 ka = __half22float2(kp[0]), kb = __half22float2(kp[1]);
+      float dot = qa.x * ka.x + qa.y * ka.y + qb.x * kb.x + qb.y * kb.y;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      dot = mk[m] ? -INFINITY : dot * scale;
+      sc[m] = dot;
+      mx = fmaxf(mx, dot);
+    }
+    float sum = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+    for (int m = 0; m < Mt; ++m) {
+      const float p = (mx == -INFINITY) ? 0.f : __expf(sc[m] - mx);
+      sum += p;
+      const __half2* vp = reinterpret_cast<const __half2*>(sV + m * 128 + lane * 4);
+      const float2 va = __half22float2(vp[0]), vb = __half22float2(vp[1]);
+      o0 = fmaf(p, va.x, o0); o1 = fmaf(p, va.y, o1); o2 = fmaf(p, vb.x, o2); o3 = fmaf(p, vb.y, o3);
+    }
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    o0 *= inv; o1 *= inv; o2 *= inv; o3 *= inv;
+    __half2* op = reinterpret_cast<__half2*>(out16 + row * 2 * d + h * 128 + lane * 4);
+    const __half2 h01 = __floats2half2_rn(o0, o1), h23 = __floats2half2_rn(o2, o3);
+    op[0] = h01;
+    op[1] = h23;
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    __half2* lp = op + d / 2;
+    lp[0] = __floats2half2_rn(o0 - f01.x, o1 - f01.y);
+    lp[1] = __floats2half2_rn(o2 - f23.x, o3 - f23.y);
   }
 }
 

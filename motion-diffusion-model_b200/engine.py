@@ -25,7 +25,7 @@ class Engine:
     """One engine per model instance (weights + workspace live on the current CUDA device)."""
 
     def __init__(self, *, arch, latent_dim, ff_size, num_layers, num_heads, njoints, nfeats, cond_mode, cond_dim,
-                 num_actions, mask_frames, pos_embed_max_len, temb_rows):
+                 num_actions, mask_frames, pos_embed_max_len, temb_rows, context_len=0):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("b200mdm needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -33,7 +33,9 @@ class Engine:
         self.cfg = _lib.Config(arch=_lib.ARCH[arch], latent_dim=latent_dim, ff_size=ff_size, num_layers=num_layers,
                                num_heads=num_heads, njoints=njoints, nfeats=nfeats, cond_mode=cm, cond_dim=cond_dim,
                                num_actions=num_actions, mask_frames=int(bool(mask_frames)),
-                               pos_embed_max_len=pos_embed_max_len, temb_rows=temb_rows)
+                               pos_embed_max_len=pos_embed_max_len, temb_rows=temb_rows, context_len=context_len)
+        self.dec = arch == "trans_dec"
+        self.context_len = context_len
         h = ctypes.c_void_p()
         check(self.lib.b200mdm_create(ctypes.byref(self.cfg), ctypes.byref(h)))
         self.h = h
@@ -80,6 +82,8 @@ class Engine:
     def set_cond(self, batch, nframes, y, guided, device):
         """Canonicalise model_kwargs['y'] (data_loaders/tensors.py:22-64 schema).  `guided` => CFG pair."""
         text_embed = y.get("text_embed") if y is not None else None
+        if self.dec:
+            return self._set_cond_dec(batch, nframes, y, guided, device)
         if isinstance(text_embed, tuple):
             raise NotImplementedError("BERT (tokens, mask) conditioning belongs to the trans_dec path")
         lengths = y.get("lengths") if y is not None else None
@@ -117,6 +121,52 @@ class Engine:
                                         int(uncond), None if ac is None else ac.ctypes.data_as(ctypes.c_void_p),
                                         _stream()))
         self._keep["cond"] = (te, sc)
+        self.batch, self.nframes = batch, nframes
+
+    def _set_cond_dec(self, batch, nframes, y, guided, device):
+        """DiP: y['text_embed'] = (BERT tokens [Mt,B,768], padding mask [B,Mt] True = pad), y['prefix'] [B,J,F,ctx]
+        (reference model/mdm.py:203-206,210-217,264)."""
+        te = y.get("text_embed")
+        if not isinstance(te, tuple):
+            raise RuntimeError("trans_dec (DiP) needs y['text_embed'] = (tokens, mask) from bert_encode_text "
+                               "(model/mdm.py:180-187)")
+        enc, tmask = te
+        enc = enc.detach().to(device=device, dtype=torch.float32)
+        if enc.shape[1] == 1 and batch > 1:
+            enc = enc.expand(-1, batch, -1)
+        enc = enc.contiguous()
+        if tmask.shape[0] == 1 and batch > 1:                  # model/mdm.py:215-216
+            tmask = torch.repeat_interleave(tmask, batch, dim=0)
+        Mt = enc.shape[0]
+        assert enc.shape == (Mt, batch, self.cfg.cond_dim) and tuple(tmask.shape) == (batch, Mt), (enc.shape, tmask.shape)
+        tm = np.ascontiguousarray(tmask.detach().cpu().numpy().astype(np.uint8))
+        lengths, mask = y.get("lengths"), y.get("mask")
+        if mask is not None and mask.shape[-1] <= 1:
+            lengths = None
+        elif lengths is None and mask is not None:
+            lengths = mask.reshape(mask.shape[0], -1).sum(-1)
+        ln = None
+        if lengths is not None:
+            ln = np.ascontiguousarray(lengths.detach().reshape(-1).cpu().numpy().astype(np.int64))
+            assert ln.shape[0] == batch
+        scale = y.get("scale") if guided else None
+        if guided and scale is None:
+            raise AssertionError("ClassifierFreeSampleModel needs y['scale'] (sampler_util.py:34)")
+        sc = None
+        if scale is not None:
+            sc = scale.detach().to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+            assert sc.shape[0] == batch
+        check(self.lib.b200mdm_set_cond_dec(self.h, batch, nframes, _ptr(enc), tm.ctypes.data_as(ctypes.c_void_p), Mt,
+                                            None if ln is None else ln.ctypes.data_as(ctypes.c_void_p), _ptr(sc),
+                                            int(bool(y.get("uncond", False))), _stream()))
+        pf = None
+        if self.context_len > 0:
+            if "prefix" not in y:
+                raise KeyError("prefix completion needs y['prefix'] [B, njoints, nfeats, context_len] (model/mdm.py:204)")
+            pf = y["prefix"].detach().to(device=device, dtype=torch.float32).contiguous()
+            assert tuple(pf.shape) == (batch, self.cfg.njoints, self.cfg.nfeats, self.context_len), pf.shape
+            check(self.lib.b200mdm_set_prefix(self.h, _ptr(pf), _stream()))
+        self._keep["cond"] = (enc, sc, pf)
         self.batch, self.nframes = batch, nframes
 
     def set_inpaint(self, mask, motion):

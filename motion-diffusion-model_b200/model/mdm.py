@@ -5,9 +5,11 @@ shapes, so reference checkpoints load with the reference's own `load_state_dict(
 (utils/model_util.py:8-15).  The parameters are plain storage: `forward` never multiplies by them in PyTorch.
 It uploads them once into the B200 engine (fp16 repack) and calls `b200mdm_denoise`.
 
-Implemented: arch='trans_enc', cond_mode in {no_cond, text (CLIP features), action}, hml_vec / rot6d / xyz data_rep.
-Not implemented (raise): arch 'gru', data_rep 'rot_vel', multi-target conditioning (CLoSD), and -- in this
-revision -- arch 'trans_dec' (DiP), which is the first "next" row of SURVEY.md section 8f.
+Implemented: arch='trans_enc' with cond_mode in {no_cond, text (CLIP features), action}; arch='trans_dec' with
+text_encoder_type='bert' (DiP: BERT token memory, prefix completion, model/mdm.py:203-206,255-270); hml_vec / rot6d /
+xyz data_rep.
+Not implemented (raise): arch 'gru', data_rep 'rot_vel', multi-target conditioning (CLoSD), emb_trans_dec,
+emb_policy != 'add', trans_dec with CLIP features.
 """
 import numpy as np
 import torch
@@ -52,8 +54,13 @@ def _spec(arch, d, ff, layers, input_feats, cond_mode, cond_dim, num_actions):
         s += [("embed_text.weight", (d, cond_dim), "lin"), ("embed_text.bias", (d,), "lin")]
     if "action" in cond_mode:
         s += [("embed_action.action_embedding", (num_actions, d), "normal")]
+    dec = arch == "trans_dec"
     for l in range(layers):
-        p = "seqTransEncoder.layers.%d." % l
+        p = ("seqTransDecoder.layers.%d." if dec else "seqTransEncoder.layers.%d.") % l
+        if dec:   # nn.TransformerDecoderLayer: cross-attention block + third norm
+            s += [(p + "multihead_attn.in_proj_weight", (3 * d, d), "xavier"), (p + "multihead_attn.in_proj_bias", (3 * d,), "zero"),
+                  (p + "multihead_attn.out_proj.weight", (d, d), "lin"), (p + "multihead_attn.out_proj.bias", (d,), "zero"),
+                  (p + "norm3.weight", (d,), "one"), (p + "norm3.bias", (d,), "zero")]
         s += [(p + "self_attn.in_proj_weight", (3 * d, d), "xavier"), (p + "self_attn.in_proj_bias", (3 * d,), "zero"),
               (p + "self_attn.out_proj.weight", (d, d), "lin"), (p + "self_attn.out_proj.bias", (d,), "zero"),
               (p + "linear1.weight", (ff, d), "lin"), (p + "linear1.bias", (ff,), "lin"),
@@ -106,15 +113,23 @@ class MDM(_Bag):
         self.rot2xyz = _identity_rot2xyz            # hml_vec: Rotation2xyz is an identity (rotation2xyz.py:20-21)
         self.clip_model = None                      # the frozen text tower stays outside the engine
 
-        if arch != "trans_enc":
-            raise NotImplementedError("arch=%r: this revision implements the trans_enc denoiser (trans_dec/DiP is the "
-                                      "next row of SURVEY.md 8f; gru is an ablation and out of scope)" % (arch,))
+        if arch not in ("trans_enc", "trans_dec"):
+            raise NotImplementedError("arch=%r: the engine implements the trans_enc and trans_dec (DiP) denoisers; gru is "
+                                      "an ablation and out of scope" % (arch,))
         if activation != "gelu":
             raise NotImplementedError("the fused FFN epilogue implements exact GELU only (model_util.py:63)")
-        if data_rep == "rot_vel" or self.multi_target_cond or self.emb_policy != "add" or self.is_prefix_comp:
-            raise NotImplementedError("rot_vel / multi-target / prefix-completion variants are outside the hot path")
-        if "text" in self.cond_mode and self.text_encoder_type != "clip":
-            raise NotImplementedError("BERT text conditioning requires arch='trans_dec' (model/mdm.py:114)")
+        if data_rep == "rot_vel" or self.multi_target_cond or self.emb_policy != "add":
+            raise NotImplementedError("rot_vel / multi-target / emb_policy='cat' variants are outside the hot path")
+        if arch == "trans_enc":
+            if self.is_prefix_comp:
+                raise NotImplementedError("prefix completion is implemented for arch='trans_dec' (DiP) only")
+            if "text" in self.cond_mode and self.text_encoder_type != "clip":
+                raise AssertionError("BERT text conditioning requires arch='trans_dec' (model/mdm.py:114)")
+        else:
+            if "text" not in self.cond_mode or self.text_encoder_type != "bert" or emb_trans_dec:
+                raise NotImplementedError("arch='trans_dec' is implemented for the DiP configuration: cond_mode='text', "
+                                          "text_encoder_type='bert', emb_trans_dec=False")
+            self.clip_dim = 768                     # model/mdm.py:117
 
         for key, shape, kind in _spec(arch, latent_dim, ff_size, num_layers, self.input_feats, self.cond_mode,
                                       self.clip_dim, num_actions):
@@ -140,11 +155,15 @@ class MDM(_Bag):
 
     # ------------------------------------------------------------------ text
     def encode_text(self, raw_text):
-        """clip_encode_text (reference model/mdm.py:163-178).  The CLIP tower is third-party, frozen, and runs once
-        per loop outside the replaced path; plug it in with `model.clip_model = clip.load(...)[0]`."""
+        """clip_encode_text / bert_encode_text (reference model/mdm.py:163-187).  The text tower is third-party, frozen,
+        and runs once per loop outside the replaced path; plug it in with `model.clip_model = clip.load(...)[0]`
+        (or the DistilBERT wrapper for DiP)."""
         if self.clip_model is None:
-            raise RuntimeError("no text encoder attached: pass y['text_embed'] (cached CLIP features [1,B,512]) or "
-                               "set model.clip_model")
+            raise RuntimeError("no text encoder attached: pass y['text_embed'] (cached CLIP features [1,B,512], or the "
+                               "(tokens [Mt,B,768], padding mask [B,Mt]) pair for DiP) or set model.clip_model")
+        if self.text_encoder_type == "bert":
+            enc_text, mask = self.clip_model(raw_text)          # mask: True = token present
+            return enc_text.permute(1, 0, 2), ~mask
         import clip  # noqa -- only when a real encoder was attached
         device = next(self.parameters()).device
         if self.dataset in ("humanml", "kit"):
@@ -166,7 +185,8 @@ class MDM(_Bag):
                                       num_layers=self.num_layers, num_heads=self.num_heads, njoints=self.njoints,
                                       nfeats=self.nfeats, cond_mode=self.cond_mode, cond_dim=self.clip_dim,
                                       num_actions=max(1, self.num_actions), mask_frames=self.mask_frames,
-                                      pos_embed_max_len=self.pos_embed_max_len, temb_rows=self.temb_rows)
+                                      pos_embed_max_len=self.pos_embed_max_len, temb_rows=self.temb_rows,
+                                      context_len=self.context_len if self.arch == "trans_dec" else 0)
             self._engine_device = dev
             self._engine_dirty = True
         if self._engine_dirty:

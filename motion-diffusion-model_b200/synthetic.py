@@ -87,3 +87,15 @@ def synthetic_inputs(batch, njoints=263, nfeats=1, nframes=196, steps=50, cond_d
     if not torch.is_tensor(scale):
         scale = torch.full((batch,), float(scale), dtype=torch.float32)
     return dict(tape=tape, text_embed=text_embed, lengths=lengths, mask=mask, scale=scale)
+
+
+def synthetic_dip_inputs(batch, n_tokens, context_len, njoints=263, nfeats=1, cond_dim=768, seed=3):
+    """Deterministic DiP conditioning in the reference's layouts (model/mdm.py:180-187,204): BERT token features
+    [n_tokens, B, 768], ragged padding mask [B, n_tokens] (True = padding; sample 0 has none), prefix [B, J, F, ctx]."""
+    g = torch.Generator().manual_seed(seed)
+    enc = torch.randn(n_tokens, batch, cond_dim, generator=g)
+    tmask = torch.zeros(batch, n_tokens, dtype=torch.bool)
+    for b in range(1, batch):
+        tmask[b, n_tokens - (b * 2) % n_tokens:] = True
+    prefix = torch.randn(batch, njoints, nfeats, context_len, generator=g)
+    return enc, tmask, prefix

@@ -15,6 +15,8 @@ Files
                  inpainting loop output, skip_timesteps/init_image output
   enc_c1.npz     BASELINE config 1 shape: L=8, B=1, T=196, 50 steps, CFG 2.5 -> final sample
   a2m_small.npz  action-conditioned trans_enc (humanact12 shape 25x6, 12 classes), no CFG, 3 steps
+  dip_small.npz  trans_dec + BERT-token memory + prefix completion (DiP): L=2, ctx 20 + pred 40, 3 steps, ragged text
+                 padding mask, per-sample scales: one CFG forward and the p_sample_loop output
 """
 import importlib
 import os
@@ -167,6 +169,30 @@ def gen_a2m_small():
     print("a2m_small.npz:", tuple(ref.shape))
 
 
+def gen_dip_small():
+    """trans_dec + bert dims (DiP): L=2, ctx 20 + pred 40, 3 steps, ragged text mask, per-sample scales."""
+    ns = rh.load_reference()
+    L, steps, B, ctx, pred, Mt = 2, 3, 3, 20, 40, 7
+    args = rh.default_args(layers=L, diffusion_steps=steps, arch="trans_dec", text_encoder_type="bert", context_len=ctx, pred_len=pred)
+    sd = syn.synthetic_state_dict(arch="trans_dec", num_layers=L, cond_dim=768, seed=4)
+    model, diff = rh.build(args, state_dict=sd)
+    cfg = ns.sampler_util.ClassifierFreeSampleModel(model)
+    enc, tmask, prefix = syn.synthetic_dip_inputs(B, Mt, ctx)
+    inp = syn.synthetic_inputs(B, nframes=pred, steps=steps, seed=13, lengths=[40, 33, 12], scale=torch.tensor([7.5, 2.0, 1.0]))
+
+    def y():
+        return dict(mask=inp["mask"].clone(), lengths=inp["lengths"], text_embed=(enc, tmask), scale=inp["scale"], prefix=prefix)
+    out = {"meta": np.array(["DiP L=2 steps=3 B=3 ctx=20 pred=40 Mt=7 weights_seed=4 inputs_seed=13 dip_seed=3 lengths=40,33,12 scales=7.5,2,1"])}
+    with torch.no_grad():
+        t = torch.full((B,), 1, dtype=torch.long)
+        out["fwd_cfg"] = cfg(inp["tape"][0], t, y=y()).numpy()
+        with rh.noise_tape(inp["tape"]):
+            out["ddpm"] = diff.p_sample_loop(cfg, (B, 263, 1, pred), clip_denoised=False, model_kwargs={"y": y()}).numpy()
+    out["text_mask"] = tmask.numpy()
+    np.savez_compressed(os.path.join(OUT, "dip_small.npz"), **out)
+    print("dip_small.npz:", {k: v.shape for k, v in out.items() if k != "meta"})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -175,3 +201,4 @@ if __name__ == "__main__":
     gen_enc_small()
     gen_enc_c1()
     gen_a2m_small()
+    gen_dip_small()

@@ -193,3 +193,76 @@ def sample_loop(W, tables, timestep_map, tape, cond, scale, lengths=None, mask_f
         if collect is not None:
             collect.append(x.clone())
     return x
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# trans_dec (DiP) -- model/mdm.py:203-206, 255-270, 278-280; torch nn.TransformerDecoderLayer (post-norm):
+#   x = LN1(x + SelfAttn(x)); x = LN2(x + CrossAttn(x, memory)); x = LN3(x + FFN(x))
+def _mha_cross(h, mem, lw, mem_mask, H, cast=None):
+    """nn.MultiheadAttention with query = h [B,S,d], key = value = mem [B,Mt,d]; mem_mask [B,Mt] True = ignore."""
+    B, S, d = h.shape
+    Mt = mem.shape[1]
+    dh = d // H
+    wq, wk, wv = lw["in_w"].split(d, dim=0)
+    bq, bk, bv = lw["in_b"].split(d, dim=0)
+    q = _lin(h, wq, bq, cast).view(B, S, H, dh).transpose(1, 2)
+    k = _lin(mem, wk, bk, cast).view(B, Mt, H, dh).transpose(1, 2)
+    v = _lin(mem, wv, bv, cast).view(B, Mt, H, dh).transpose(1, 2)
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
+    if mem_mask is not None:
+        s = s.masked_fill(mem_mask[:, None, None, :], float("-inf"))
+    a = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B, S, d)
+    return _lin(a, lw["out_w"], lw["out_b"], cast)
+
+
+def decoder_stack(W, h, mem, tgt_keymask, mem_keymask, cast=None):
+    d = W.d
+    for l in range(W.L):
+        p = "seqTransDecoder.layers.%d." % l
+        sa = dict(in_w=W[p + "self_attn.in_proj_weight"], in_b=W[p + "self_attn.in_proj_bias"],
+                  out_w=W[p + "self_attn.out_proj.weight"], out_b=W[p + "self_attn.out_proj.bias"])
+        ca = dict(in_w=W[p + "multihead_attn.in_proj_weight"], in_b=W[p + "multihead_attn.in_proj_bias"],
+                  out_w=W[p + "multihead_attn.out_proj.weight"], out_b=W[p + "multihead_attn.out_proj.bias"])
+        h = F.layer_norm(h + _mha_self(h, sa, tgt_keymask, W.H, cast), (d,), W[p + "norm1.weight"], W[p + "norm1.bias"], 1e-5)
+        h = F.layer_norm(h + _mha_cross(h, mem, ca, mem_keymask, W.H, cast), (d,), W[p + "norm2.weight"], W[p + "norm2.bias"], 1e-5)
+        f = _lin(F.gelu(_lin(h, W[p + "linear1.weight"], W[p + "linear1.bias"], cast)), W[p + "linear2.weight"], W[p + "linear2.bias"], cast)
+        h = F.layer_norm(h + f, (d,), W[p + "norm3.weight"], W[p + "norm3.bias"], 1e-5)
+    return h
+
+
+def denoise_dec(W, x, t_model, enc_text, text_mask, prefix, lengths=None, mask_frames=True, uncond=False, cast=None):
+    """MDM.forward for arch=trans_dec, text_encoder_type=bert, emb_trans_dec=False, prefix completion.
+
+    x [B,J,F,pred]; prefix [B,J,F,ctx]; enc_text [Mt,B,768]; text_mask [B,Mt] True = padding;
+    lengths [B] valid frames of x (the context frames are always valid, mdm.py:204-206)."""
+    B, J, Fe, Tp = x.shape
+    ctx = prefix.shape[-1]
+    d = W.d
+    temb = timestep_embedding(W, t_model)
+    enc = torch.zeros_like(enc_text) if uncond else enc_text
+    mem = _lin(enc.permute(1, 0, 2), W["embed_text.weight"], W["embed_text.bias"], None) + temb[None, None, :]   # [B,Mt,d]
+    xf = torch.cat([prefix, x], dim=-1)
+    T = ctx + Tp
+    frames = xf.permute(0, 3, 1, 2).reshape(B, T, J * Fe)
+    h = _lin(frames, W["input_process.poseEmbedding.weight"], W["input_process.poseEmbedding.bias"], cast) + W.pe[:T][None]
+    keymask = None
+    if mask_frames and lengths is not None and T > 1:
+        keymask = torch.arange(T)[None, :] >= (lengths[:, None] + ctx)
+    h = decoder_stack(W, h, mem, keymask, text_mask, cast)[:, ctx:]
+    out = _lin(h, W["output_process.poseFinal.weight"], W["output_process.poseFinal.bias"], cast)
+    return out.reshape(B, Tp, J, Fe).permute(0, 2, 3, 1).contiguous()
+
+
+def cfg_denoise_dec(W, x, t_model, enc_text, text_mask, prefix, scale, lengths=None, mask_frames=True, cast=None):
+    oc = denoise_dec(W, x, t_model, enc_text, text_mask, prefix, lengths, mask_frames, False, cast)
+    ou = denoise_dec(W, x, t_model, enc_text, text_mask, prefix, lengths, mask_frames, True, cast)
+    return ou + scale.view(-1, 1, 1, 1) * (oc - ou)
+
+
+def sample_loop_dec(W, tables, timestep_map, tape, enc_text, text_mask, prefix, scale, lengths=None, mask_frames=True, cast=None):
+    n = len(tables["betas"])
+    x = tape[0].clone()
+    for k, i in enumerate(range(n - 1, -1, -1)):
+        x0 = cfg_denoise_dec(W, x, int(timestep_map[i]), enc_text, text_mask, prefix, scale, lengths, mask_frames, cast)
+        x, _ = p_sample_step(tables, x0, x, i, tape[1 + k])
+    return x

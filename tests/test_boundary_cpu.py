@@ -58,9 +58,49 @@ def test_api_surface_matches_reference():
 
 
 def test_unsupported_configs_raise():
-    for over in (dict(arch="gru"), dict(arch="trans_dec", text_encoder_type="bert")):
+    for over in (dict(arch="gru"), dict(arch="trans_dec", text_encoder_type="clip"),
+                 dict(arch="trans_dec", text_encoder_type="bert", emb_trans_dec=True),
+                 dict(arch="trans_enc", context_len=20, pred_len=40)):
         with pytest.raises(NotImplementedError):
             b200mdm.create_model_and_diffusion(default_args(layers=1, **over), SimpleNamespace(dataset=SimpleNamespace()))
+
+
+def test_dip_model_keys_match_reference_layout():
+    """trans_dec / BERT (DiP): parameter names and shapes of nn.TransformerDecoderLayer (model/mdm.py:87-96,110-119)."""
+    args = default_args(layers=2, arch="trans_dec", text_encoder_type="bert", context_len=20, pred_len=40)
+    model, _ = b200mdm.create_model_and_diffusion(args, SimpleNamespace(dataset=SimpleNamespace()))
+    assert model.clip_dim == 768 and model.is_prefix_comp and model.total_len == 60
+    sd = model.state_dict()
+    want = b200mdm.synthetic_state_dict(arch="trans_dec", num_layers=2, cond_dim=768, seed=4)
+    assert set(sd.keys()) == set(want.keys())
+    for k, v in want.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    assert "seqTransDecoder.layers.1.multihead_attn.in_proj_weight" in sd and "seqTransDecoder.layers.0.norm3.bias" in sd
+    b200mdm.load_model_wo_clip(model, want)
+
+
+def test_autoregressive_sampler_chunks():
+    """AutoRegressiveSampler (utils/sampler_util.py:41-81): chunk count, prefix hand-over, cropping -- with a stub
+    sample_fn, no GPU."""
+    args = SimpleNamespace(pred_len=40, context_len=20, autoregressive_include_prefix=False)
+    seen = []
+
+    def sample_fn(model, shape, **kw):
+        y = kw["model_kwargs"]["y"]
+        seen.append((tuple(shape), y["prefix"].clone()))
+        return torch.full(shape, float(len(seen))) + torch.arange(shape[-1]).float() / 100
+
+    prefix = torch.zeros(2, 263, 1, 20)
+    y = {"prefix": prefix, "text": ["a", "b"]}
+    out = b200mdm.AutoRegressiveSampler(args, sample_fn, required_frames=196).sample(None, (2, 263, 1, 196), model_kwargs={"y": y})
+    assert out.shape == (2, 263, 1, 196) and len(seen) == 5
+    assert all(s[0] == (2, 263, 1, 40) for s in seen)
+    assert torch.equal(seen[0][1], prefix) and y["prefix"] is prefix
+    assert torch.equal(seen[2][1], torch.full((2, 263, 1, 20), 2.0) + torch.arange(20, 40).float() / 100)
+    assert float(out[0, 0, 0, 0]) == 1.0 and abs(float(out[0, 0, 0, 195]) - 5.35) < 1e-6
+    args.autoregressive_include_prefix = True
+    out = b200mdm.AutoRegressiveSampler(args, sample_fn, required_frames=100).sample(None, (2, 263, 1, 100), model_kwargs={"y": y})
+    assert out.shape == (2, 263, 1, 100) and torch.equal(out[..., :20], prefix)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

@@ -76,6 +76,26 @@ def test_a2m_vs_golden(golden):
     assert rel_err(o, g["sample"]) < TOL
 
 
+def _setup_dip():
+    L, steps, B, ctx, pred, Mt = 2, 3, 3, 20, 40, 7
+    W = mo.OracleWeights(b200mdm.synthetic_state_dict(arch="trans_dec", num_layers=L, cond_dim=768, seed=4), L)
+    enc, tmask, prefix = b200mdm.synthetic_dip_inputs(B, Mt, ctx)
+    inp = b200mdm.synthetic_inputs(B, nframes=pred, steps=steps, seed=13, lengths=[40, 33, 12], scale=torch.tensor([7.5, 2.0, 1.0]))
+    return W, enc, tmask, prefix, inp
+
+
+def test_dip_vs_golden(golden):
+    """trans_dec + BERT memory + prefix completion (DiP): decoder restatement against the unmodified reference."""
+    g = golden("dip_small.npz")
+    W, enc, tmask, prefix, inp = _setup_dip()
+    assert np.array_equal(tmask.numpy(), g["text_mask"])
+    out = mo.cfg_denoise_dec(W, inp["tape"][0], 1, enc, tmask, prefix, inp["scale"], inp["lengths"])
+    assert rel_err(out, g["fwd_cfg"]) < TOL
+    tabs = so.diffusion_tables(so.named_betas("cosine", 3))
+    o = mo.sample_loop_dec(W, tabs, [0, 1, 2], inp["tape"], enc, tmask, prefix, inp["scale"], inp["lengths"])
+    assert rel_err(o, g["ddpm"]) < TOL
+
+
 @pytest.mark.reference
 def test_oracle_vs_live_reference():
     """Build container only: run the unmodified reference next to the oracle on fresh seeds (not the fixtures)."""

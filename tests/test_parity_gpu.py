@@ -183,3 +183,99 @@ def test_generator_stream_matches_reference_draw_order():
     tape = torch.stack([torch.randn_like(xT) for _ in range(4)])
     b = diffusion.p_sample_loop(cfg, shape, noise=xT, clip_denoised=False, model_kwargs={"y": _y(inp)}, noise_tape=tape)
     assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# DiP: arch=trans_dec, BERT token memory, prefix completion
+def _dip(layers, steps, seed, ctx=20, pred=40):
+    args = default_args(layers=layers, diffusion_steps=steps, arch="trans_dec", text_encoder_type="bert", context_len=ctx,
+                        pred_len=pred)
+    model, diffusion = b200mdm.create_model_and_diffusion(args, SimpleNamespace(dataset=SimpleNamespace()))
+    sd = b200mdm.synthetic_state_dict(arch="trans_dec", num_layers=layers, cond_dim=768, seed=seed)
+    b200mdm.load_model_wo_clip(model, sd)
+    model.to("cuda").eval()
+    return b200mdm.ClassifierFreeSampleModel(model), model, diffusion, sd, args
+
+
+def _dip_y(inp, enc, tmask, prefix, scale=True):
+    y = dict(mask=inp["mask"].cuda(), lengths=inp["lengths"].cuda(), text_embed=(enc.cuda(), tmask.cuda()), prefix=prefix.cuda())
+    if scale:
+        y["scale"] = inp["scale"].cuda()
+    return y
+
+
+def test_dip_vs_reference_golden(golden):
+    g = golden("dip_small.npz")
+    cfg, model, diffusion, _, _ = _dip(2, 3, 4)
+    enc, tmask, prefix = b200mdm.synthetic_dip_inputs(3, 7, 20)
+    inp = b200mdm.synthetic_inputs(3, nframes=40, steps=3, seed=13, lengths=[40, 33, 12], scale=torch.tensor([7.5, 2.0, 1.0]))
+    x = inp["tape"][0].cuda()
+    t = torch.full((3,), 1, dtype=torch.long, device="cuda")
+    y = _dip_y(inp, enc, tmask, prefix)
+    assert rel_err(cfg(x, t, y=y), g["fwd_cfg"]) < RTOL
+    assert y["mask"].shape[-1] == 40                      # y is not mutated
+    tape, xT = _tape(inp)
+    outs = []
+    for use_graph in (False, True):
+        out = diffusion.p_sample_loop(cfg, (3, 263, 1, 40), noise=xT, clip_denoised=False, model_kwargs={"y": y},
+                                      noise_tape=tape, use_graph=use_graph)
+        assert rel_err(out, g["ddpm"]) < RTOL
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    y.pop("prefix")
+    with pytest.raises(KeyError):
+        cfg(x, t, y=y)
+
+
+def test_dip_full_depth_vs_oracle():
+    """DiP at its released depth (8 layers, 20 + 40 frames), fresh seeds: single forwards (cond / uncond / CFG) and a
+    5-step loop against the fp32 oracle."""
+    from oracle import mdm_oracle as mo, schedule_oracle as so
+    B, ctx, pred, Mt, steps = 5, 20, 40, 12, 5
+    cfg, model, diffusion, sd, _ = _dip(8, steps, 21)
+    W = mo.OracleWeights(sd, 8)
+    enc, tmask, prefix = b200mdm.synthetic_dip_inputs(B, Mt, ctx, seed=31)
+    inp = b200mdm.synthetic_inputs(B, nframes=pred, steps=steps, seed=32, lengths=[40, 40, 31, 7, 1],
+                                   scale=torch.tensor([7.5, 7.5, 2.5, 1.0, 0.0]))
+    x = inp["tape"][0]
+    t = torch.tensor([0, 1, 2, 3, 4])
+    for uncond in (False, True):
+        y = _dip_y(inp, enc, tmask, prefix, scale=False)
+        y["uncond"] = uncond
+        want = torch.stack([mo.denoise_dec(W, x[b:b + 1], int(t[b]), enc[:, b:b + 1], tmask[b:b + 1], prefix[b:b + 1],
+                                           inp["lengths"][b:b + 1], True, uncond)[0] for b in range(B)])
+        assert rel_err(model(x.cuda(), t.cuda(), y=y), want) < RTOL, uncond
+    tabs = so.diffusion_tables(so.named_betas("cosine", steps))
+    want = mo.sample_loop_dec(W, tabs, list(range(steps)), inp["tape"], enc, tmask, prefix, inp["scale"], inp["lengths"])
+    tape, xT = _tape(inp)
+    out = diffusion.p_sample_loop(cfg, (B, 263, 1, pred), noise=xT, clip_denoised=False,
+                                  model_kwargs={"y": _dip_y(inp, enc, tmask, prefix)}, noise_tape=tape)
+    assert rel_err(out, want) < RTOL
+
+
+def test_dip_autoregressive_vs_oracle():
+    """AutoRegressiveSampler over the engine: 3 chunks of 40 frames cropped to 100, prefix handed from chunk to chunk."""
+    from oracle import mdm_oracle as mo, schedule_oracle as so
+    B, ctx, pred, Mt, steps, need = 2, 20, 40, 9, 3, 100
+    cfg, model, diffusion, sd, args = _dip(2, steps, 22)
+    W = mo.OracleWeights(sd, 2)
+    enc, tmask, prefix = b200mdm.synthetic_dip_inputs(B, Mt, ctx, seed=33)
+    scale = torch.tensor([7.5, 2.5])
+    chunks = [b200mdm.synthetic_inputs(B, nframes=pred, steps=steps, seed=40 + i, scale=scale) for i in range(3)]
+    tabs = so.diffusion_tables(so.named_betas("cosine", steps))
+    cur, buf = prefix, []
+    for c in chunks:
+        s = mo.sample_loop_dec(W, tabs, list(range(steps)), c["tape"], enc, tmask, cur, scale, c["lengths"])
+        buf.append(s)
+        cur = s[..., -ctx:]
+    want = torch.cat(buf, -1)[..., :need]
+    y = dict(mask=chunks[0]["mask"].cuda(), lengths=chunks[0]["lengths"].cuda(), text_embed=(enc.cuda(), tmask.cuda()),
+             prefix=prefix.cuda(), scale=scale.cuda(), text=["a", "b"])
+    y.pop("text")                                           # cached embeddings only: no text tower on the box
+    sampler = b200mdm.AutoRegressiveSampler(args, diffusion.p_sample_loop, required_frames=need)
+    out = sampler.sample(cfg, (B, 263, 1, need), clip_denoised=False, model_kwargs={"y": y},
+                         noise=torch.stack([c["tape"][0] for c in chunks]).cuda(),
+                         noise_tape=torch.stack([torch.stack(c["tape"][1:]) for c in chunks]).cuda())
+    assert out.shape == (B, 263, 1, need)
+    assert rel_err(out, want) < RTOL
+    assert torch.equal(y["prefix"], prefix.cuda())
