@@ -279,3 +279,71 @@ def test_dip_autoregressive_vs_oracle():
     assert out.shape == (B, 263, 1, need)
     assert rel_err(out, want) < RTOL
     assert torch.equal(y["prefix"], prefix.cuda())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs 3 and 4 at their full sizes: the whole batch runs on the GPU, the fp32 oracle follows a few
+# samples of it (every sample is independent of its batch neighbours, so a subset is a complete check of those rows).
+def _gpu_tape(n_run, shape, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    xT = torch.randn(*shape, device="cuda", generator=g)
+    tape = torch.randn(n_run, *shape, device="cuda", generator=g)
+    return xT, tape
+
+
+def test_dip_config_b128_autoregressive():
+    """BASELINE config 3: DiP, B=128, 10 diffusion steps per 40-frame chunk, guidance 7.5 -- 3 chunks (120 -> 100 frames)."""
+    from oracle import mdm_oracle as mo, schedule_oracle as so
+    B, ctx, pred, Mt, steps, need, nchunk = 128, 20, 40, 16, 10, 100, 3
+    cfg, model, diffusion, sd, args = _dip(8, steps, 23)
+    enc, tmask, prefix = b200mdm.synthetic_dip_inputs(B, Mt, ctx, seed=35)
+    scale = torch.full((B,), 7.5)
+    lengths = torch.full((B,), pred, dtype=torch.long)
+    shape = (B, 263, 1, pred)
+    noise, tapes = zip(*[_gpu_tape(steps, shape, 50 + i) for i in range(nchunk)])
+    y = dict(mask=torch.ones(B, 1, 1, pred, dtype=torch.bool, device="cuda"), lengths=lengths.cuda(),
+             text_embed=(enc.cuda(), tmask.cuda()), prefix=prefix.cuda(), scale=scale.cuda())
+    sampler = b200mdm.AutoRegressiveSampler(args, diffusion.p_sample_loop, required_frames=need)
+    out = sampler.sample(cfg, (B, 263, 1, need), clip_denoised=False, model_kwargs={"y": y}, noise=torch.stack(noise),
+                         noise_tape=torch.stack(tapes))
+    again = sampler.sample(cfg, (B, 263, 1, need), clip_denoised=False, model_kwargs={"y": y}, noise=torch.stack(noise),
+                           noise_tape=torch.stack(tapes))
+    assert out.shape == (B, 263, 1, need) and torch.isfinite(out).all() and torch.equal(out, again)
+    W = mo.OracleWeights(sd, 8)
+    tabs = so.diffusion_tables(so.named_betas("cosine", steps))
+    idx = [0, 77, 127]
+    cur, buf = prefix[idx], []
+    for c in range(nchunk):
+        tape = [noise[c][idx].cpu()] + [tapes[c][k][idx].cpu() for k in range(steps)]
+        s = mo.sample_loop_dec(W, tabs, list(range(steps)), tape, enc[:, idx], tmask[idx], cur, scale[idx], lengths[idx])
+        buf.append(s)
+        cur = s[..., -ctx:]
+    want = torch.cat(buf, -1)[..., :need]
+    e = rel_err(out[idx], want)
+    print("DiP B=128, 3 chunks x 10 steps, guidance 7.5: relative error vs oracle", e)
+    assert e < RTOL
+
+
+def test_a2m_config_b256_1000_steps():
+    """BASELINE config 4: HumanAct12 action2motion, B=256, 60 frames, 1000 steps, no guidance: 1000 recurrent steps of
+    the fused loop (one graph replayed 1000 times) against the oracle on two samples."""
+    from oracle import mdm_oracle as mo, schedule_oracle as so
+    B, T, steps = 256, 60, 1000
+    model, _, diffusion = _build(8, steps, 5, guided=False, dataset="humanact12", cond_mask_prob=0.0)
+    sd = b200mdm.synthetic_state_dict(num_layers=8, seed=5, input_feats=150, cond_mode="action", num_actions=12)
+    shape = (B, 25, 6, T)
+    xT, tape = _gpu_tape(steps, shape, 60)
+    lengths = torch.full((B,), T, dtype=torch.long)
+    lengths[1] = 45
+    action = (torch.arange(B) % 12).view(B, 1)
+    y = dict(mask=(torch.arange(T)[None, :] < lengths[:, None]).view(B, 1, 1, T).cuda(), lengths=lengths.cuda(), action=action.cuda())
+    out = diffusion.p_sample_loop(model, shape, noise=xT, clip_denoised=False, model_kwargs={"y": y}, noise_tape=tape)
+    assert torch.isfinite(out).all()
+    idx = [1, 200]
+    W = mo.OracleWeights(sd, 8)
+    tabs = so.diffusion_tables(so.named_betas("cosine", steps))
+    tp = [xT[idx].cpu()] + [tape[k][idx].cpu() for k in range(steps)]
+    want = mo.sample_loop(W, tabs, list(range(steps)), tp, None, None, lengths[idx], action=action[idx])
+    e = rel_err(out[idx], want)
+    print("a2m B=256, 1000 steps: relative error vs oracle", e)
+    assert e < RTOL
