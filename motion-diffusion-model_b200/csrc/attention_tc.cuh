@@ -74,6 +74,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, smp = blockIdx.y, tile = blockIdx.z;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_kv);
@@ -93,6 +94,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA loader

@@ -226,14 +226,47 @@ static int init_kernel_attrs() {
   return B200MDM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ launches
+// Kernels of the sampling step are launched with programmatic stream serialization (PDL): the next kernel's CTAs are
+// scheduled as SMs drain and run their prologue (barrier init, TMEM allocation, descriptor prefetch, bias staging)
+// under the tail of the current one; every kernel calls griddepcontrol.wait before it touches global data.
+// B200MDM_PDL=0 in the environment restores plain stream order.
+static bool g_pdl_now = false;   // set while b200mdm is enqueueing a step
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200MDM_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+struct PdlScope {
+  PdlScope() { g_pdl_now = pdl_enabled(); }
+  ~PdlScope() { g_pdl_now = false; }
+};
+template <class... KArgs, class... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl_now ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...);
+}
+
 template <int BN, class Epi>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int M, int N, int K,
                        const typename Epi::Params& p, cudaStream_t s, int num_sms) {
   if (N * 4 > GEMM_BIAS_BYTES) return fail(B200MDM_ENOTIMPL, "GEMM epilogue vectors are staged for N <= %d", GEMM_BIAS_BYTES / 4);
   const int tiles = ((M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_f16_tcgen05<BN, Epi><<<grid, GEMM_THREADS, GemmSmem<BN, Epi>::TOTAL, s>>>(a, b, c, M, N, K, p);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_k(gemm_f16_tcgen05<BN, Epi>, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN, Epi>::TOTAL, s, a, b, c, M, N, K, p));
   return B200MDM_OK;
 }
 
@@ -245,8 +278,7 @@ static int launch_gemm2(const CUtensorMap& a, const CUtensorMap& b, const CUtens
   const int tiles = ((M + GEMM2_TILE_M - 1) / GEMM2_TILE_M) * ((N + GEMM2_BLOCK_N - 1) / GEMM2_BLOCK_N);
   const int max_clusters = num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  gemm2_f16_tcgen05<Epi><<<2 * clusters, GEMM_THREADS, Gemm2Smem<Epi>::TOTAL, s>>>(a, b, c, M, N, K, p);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_k(gemm2_f16_tcgen05<Epi>, dim3(2 * clusters), dim3(GEMM_THREADS), Gemm2Smem<Epi>::TOTAL, s, a, b, c, M, N, K, p));
   return B200MDM_OK;
 }
 
@@ -259,11 +291,8 @@ static int launch_gemm_resid_ln(const CUtensorMap& a, const CUtensorMap& w256, c
   const int max_clusters = num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   GemmLnParams lp{bias, gamma, beta, 1e-5f};
-  if (wide)
-    gemm_resid_ln_cluster<true><<<2 * clusters, GLN_THREADS, GemmLnSmem::TOTAL, s>>>(a, w256, h32_io, h16, M, K, lp);
-  else
-    gemm_resid_ln_cluster<false><<<2 * clusters, GLN_THREADS, GemmLnSmem::TOTAL, s>>>(a, w256, h32_io, h16, M, K, lp);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_k(wide ? gemm_resid_ln_cluster<true> : gemm_resid_ln_cluster<false>, dim3(2 * clusters), dim3(GLN_THREADS),
+                    GemmLnSmem::TOTAL, s, a, w256, h32_io, h16, M, K, lp));
   return B200MDM_OK;
 }
 
@@ -310,11 +339,8 @@ static int launch_attention_tc(const AttnMaps& m, const int* kvlen, int n_sample
   const int keys = (S + 15) & ~15;
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(ATC_DH));
   const dim3 grid(H, n_samples, (S + 127) / 128);
-  if (wide)
-    attention_tc_kernel<true><<<grid, ATC_THREADS, AttnTcSmem::total(keys), s>>>(m.q, m.kv, m.o, kvlen, S, d, keys, scale_log2);
-  else
-    attention_tc_kernel<false><<<grid, ATC_THREADS, AttnTcSmem::total(keys), s>>>(m.q, m.kv, m.o, kvlen, S, d, keys, scale_log2);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_k(wide ? attention_tc_kernel<true> : attention_tc_kernel<false>, grid, dim3(ATC_THREADS), AttnTcSmem::total(keys),
+                    s, m.q, m.kv, m.o, kvlen, S, d, keys, scale_log2));
   return B200MDM_OK;
 }
 
@@ -834,10 +860,10 @@ struct StepArgs {
 static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s, int* n_kernels) {
   const int d = e->d, ff = e->ff, B = e->B, T = e->T, S = e->S, JF = e->JF, Kp = e->Kp_in;
   int nk = 0;
+  PdlScope pdl_scope;
   {
     dim3 grid((T + 31) / 32, (JF + 31) / 32, B), block(32, 8);
-    pack_input_kernel<<<grid, block, 0, s>>>(a.x_in, e->xin16, B, JF, T, S, Kp, 3 * Kp, e->s_off);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_k(pack_input_kernel, grid, block, 0, s, a.x_in, e->xin16, B, JF, T, S, Kp, 3 * Kp, e->s_off));
     ++nk;
   }
   {
@@ -849,14 +875,13 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
     ++nk;
   }
   if (!e->dec) {
-    tok0_rows_kernel<<<e->Bp, 128, 0, s>>>(e->h32, e->h16, e->condproj, e->temb_table, e->pe,
-                                           a.explicit_t ? e->tvec : nullptr, e->tmap, e->state, B, S, d, e->cfg.temb_rows);
+    CUDA_TRY(launch_k(tok0_rows_kernel, dim3(e->Bp), dim3(128), 0, s, e->h32, e->h16, e->condproj, e->temb_table, e->pe,
+                      a.explicit_t ? e->tvec : nullptr, e->tmap, e->state, B, S, d, e->cfg.temb_rows));
   } else {
     // cross-attention memory of this step: text tokens + timestep embedding (model/mdm.py:218-220)
-    mem_build_kernel<<<dim3(e->Mt, e->Bp), 128, 0, s>>>(e->mem16, e->memproj, e->temb_table, a.explicit_t ? e->tvec : nullptr,
-                                                        e->tmap, e->state, B, e->Mt, d, e->cfg.temb_rows);
+    CUDA_TRY(launch_k(mem_build_kernel, dim3(e->Mt, e->Bp), dim3(128), 0, s, e->mem16, e->memproj, e->temb_table,
+                      a.explicit_t ? e->tvec : nullptr, e->tmap, e->state, B, e->Mt, d, e->cfg.temb_rows));
   }
-  CUDA_TRY(cudaGetLastError());
   ++nk;
   const int kw = e->kw;
   const bool wide = kw == 2;
@@ -887,9 +912,8 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
         EpiBiasF16<false>::Params p{w.bkv_c};
         TRY((launch_gemm2<EpiBiasF16<false>>(e->m_mem, w.m_wkv_c, e->m_kvc_st, e->Bp * e->Mt, 2 * d, kw * d, p, s, e->num_sms)));
       }
-      cross_attention_kernel<<<dim3(e->H, e->Bp), 128, static_cast<size_t>(e->Mt) * 512, s>>>(
-          e->qc16, e->kvc16, e->memmask, e->att16, S, e->Mt, d, 1.0f / sqrtf(128.0f));
-      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(launch_k(cross_attention_kernel, dim3(e->H, e->Bp), dim3(128), static_cast<size_t>(e->Mt) * 512, s, e->qc16,
+                        e->kvc16, e->memmask, e->att16, S, e->Mt, d, 1.0f / sqrtf(128.0f)));
       TRY(launch_gemm_resid_ln(e->m_att, w.m_wo_c_256, e->m_h32_io, e->h16, e->M, kw * d, w.bo_c, w.g2, w.be2, s, e->num_sms, wide));
       nk += 4;
     }
@@ -904,8 +928,7 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
                              e->dec ? w.be3 : w.be2, s, e->num_sms, wide));
     nk += 5;
   }
-  blend_split_kernel<<<(e->MB + 7) / 8, 256, 0, s>>>(e->h32, e->g16, e->scale, B, S, d, e->halves);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_k(blend_split_kernel, dim3((e->MB + 7) / 8), dim3(256), 0, s, e->h32, e->g16, e->scale, B, S, d, e->halves));
   ++nk;
   {
     EpiOutStep::Params p;
@@ -1017,8 +1040,9 @@ extern "C" int b200mdm_sample_loop(b200mdm_engine* e, int32_t mode, int32_t skip
       int nk = 0;
       int r = enqueue_forward(e, a, e->work, &nk);
       if (r == B200MDM_OK) {
-        step_advance_kernel<<<1, 1, 0, e->work>>>(e->state);
-        if (cudaGetLastError() != cudaSuccess) r = fail(B200MDM_ECUDA, "step_advance launch failed during capture");
+        PdlScope pdl_scope;
+        if (launch_k(step_advance_kernel, dim3(1), dim3(1), 0, e->work, e->state) != cudaSuccess)
+          r = fail(B200MDM_ECUDA, "step_advance launch failed during capture");
       }
       cudaError_t ce = cudaStreamEndCapture(e->work, &graph);
       if (r != B200MDM_OK) {
@@ -1049,8 +1073,10 @@ extern "C" int b200mdm_sample_loop(b200mdm_engine* e, int32_t mode, int32_t skip
     for (int k = 0; k < n_run; ++k) {
       int nk = 0;
       TRY(enqueue_forward(e, a, s, &nk));
-      step_advance_kernel<<<1, 1, 0, s>>>(e->state);
-      CUDA_TRY(cudaGetLastError());
+      {
+        PdlScope pdl_scope;
+        CUDA_TRY(launch_k(step_advance_kernel, dim3(1), dim3(1), 0, s, e->state));
+      }
       e->launches += nk + 1;
     }
   }

@@ -156,6 +156,7 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
 
+  pdl_launch_dependents();
   Epi::preload(ep, bias_all, N, threadIdx.x, blockDim.x);   // visible to the epilogue warps after the barrier below
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
@@ -180,6 +181,7 @@ gemm_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // the prologue above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer

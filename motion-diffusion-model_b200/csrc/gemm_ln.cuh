@@ -88,6 +88,7 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const int num_kb = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   const int col_cta = static_cast<int>(rank) * GLN_BN;
 
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < GLN_BN; i += blockDim.x) {
     prm[i] = lp.bias[col_cta + i];
     prm[GLN_BN + i] = lp.gamma[col_cta + i];
@@ -119,6 +120,7 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
   cluster_sync_all();   // the peer's barriers exist before anybody signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer

@@ -14,6 +14,8 @@ namespace b200 {
 // Row s = 0 (conditioning token slot) and the pad columns stay zero from allocation time.
 __global__ void pack_input_kernel(const float* __restrict__ x, __half* __restrict__ xin, int B, int JF, int T, int S,
                                   int Kp, int ld, int row_off) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int j0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
@@ -46,6 +48,8 @@ __global__ void tok0_rows_kernel(float* __restrict__ h32, __half* __restrict__ h
                                  const float* __restrict__ temb_table, const float* __restrict__ pe,
                                  const int* __restrict__ tvec, const int* __restrict__ tmap,
                                  const StepState* __restrict__ state, int B, int S, int d, int temb_rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int bp = blockIdx.x;
   int t = (tvec != nullptr) ? tvec[bp % B] : tmap[state->cur];
   t = min(max(t, 0), temb_rows - 1);
@@ -65,6 +69,8 @@ __global__ void pe_bias_kernel(float* __restrict__ out, const float* __restrict_
 }
 
 __global__ void step_advance_kernel(StepState* state) {
+  pdl_launch_dependents();
+  pdl_wait();
   state->done += 1;
   state->cur -= 1;
 }
@@ -128,6 +134,8 @@ __global__ void layernorm512_kernel(float* __restrict__ h32, __half* __restrict_
 //   halves == 1: v = h.       g16 row layout: [hi | lo | hi], ld = 3*d.
 __global__ void blend_split_kernel(const float* __restrict__ h32, __half* __restrict__ g16,
                                    const float* __restrict__ scale, int B, int S, int d, int halves) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B * S) return;
@@ -250,6 +258,8 @@ __global__ void mem_build_kernel(__half* __restrict__ mem16, const float* __rest
                                  const float* __restrict__ temb_table, const int* __restrict__ tvec,
                                  const int* __restrict__ tmap, const StepState* __restrict__ state, int B, int Mt, int d,
                                  int temb_rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.x, bp = blockIdx.y;
   int t = (tvec != nullptr) ? tvec[bp % B] : tmap[state->cur];
   t = min(max(t, 0), temb_rows - 1);
@@ -288,6 +298,8 @@ __global__ void permute_mbc_kernel(const float* __restrict__ src, float* __restr
 __global__ void cross_attention_kernel(const __half* __restrict__ q16, const __half* __restrict__ kv16,
                                        const unsigned char* __restrict__ mask, __half* __restrict__ out16, int S, int Mt,
                                        int d, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __half ca_smem[];   // [2][Mt][128]
   const int h = blockIdx.x, smp = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;

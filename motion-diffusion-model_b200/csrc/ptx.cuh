@@ -349,4 +349,13 @@ __device__ __forceinline__ void stg256(void* p, uint32_t a, uint32_t b, uint32_t
                ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h)
                : "memory");
 }
+
+// ---- programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its stream predecessor is still running.  pdl_launch_dependents() lets the successor's CTAs be scheduled
+// as SMs free up; pdl_wait() blocks until the predecessor grid has completed and its writes are visible.  Both are
+// no-ops for a kernel launched without the attribute.  Rule used throughout: nothing produced by an earlier kernel is
+// read, and no global memory is written, before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace b200

@@ -23,9 +23,16 @@ def shard_range(global_batch, rank, world):
 
 
 def broadcast_text_embed(text_embed, src=0, group=None):
-    """The one collective of the path: rank `src` owns the encoded prompts [1, B, C]; everybody receives them."""
+    """The one collective of the path: rank `src` owns the encoded prompts -- CLIP features [1, B, C], or for DiP the
+    (BERT tokens [Mt, B, 768], padding mask [B, Mt]) pair; everybody receives them."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.broadcast(text_embed, src=src, group=group)
+        for t in (text_embed if isinstance(text_embed, tuple) else (text_embed,)):
+            if t.dtype == torch.bool:                 # gloo / nccl broadcast byte tensors, not bool
+                b = t.to(torch.uint8)
+                dist.broadcast(b, src=src, group=group)
+                t.copy_(b.to(torch.bool))
+            else:
+                dist.broadcast(t, src=src, group=group)
     return text_embed
 
 
@@ -39,6 +46,9 @@ def shard_model_kwargs(model_kwargs, lo, hi):
     for k, v in y.items():
         if k == "text_embed" and torch.is_tensor(v):
             out[k] = v[:, lo:hi].contiguous() if v.shape[1] > 1 else v      # [1, B, C]; a single prompt is shared
+        elif k == "text_embed" and isinstance(v, tuple):                     # DiP: (tokens [Mt, B, C], mask [B, Mt])
+            tok, msk = v
+            out[k] = (tok[:, lo:hi].contiguous() if tok.shape[1] > 1 else tok, msk[lo:hi].contiguous() if msk.shape[0] > 1 else msk)
         elif k in _BATCH_KEYS and torch.is_tensor(v):
             out[k] = v[lo:hi].contiguous()
         elif k in ("text", "tokens") and isinstance(v, (list, tuple)):
@@ -61,12 +71,14 @@ def sample_sharded(sample_fn, model, shape, model_kwargs, *, n_steps, noise_mode
     B = int(shape[0])
     lo, hi = shard_range(B, rank, world)
     y = model_kwargs["y"]
-    if torch.is_tensor(y.get("text_embed")):
+    if torch.is_tensor(y.get("text_embed")) or isinstance(y.get("text_embed"), tuple):
         broadcast_text_embed(y["text_embed"], 0, group)
     local_kwargs = shard_model_kwargs(model_kwargs, lo, hi)
     local_shape = (hi - lo,) + tuple(shape[1:])
     if device is None:
-        device = y["text_embed"].device if torch.is_tensor(y.get("text_embed")) else torch.device("cpu")
+        te = y.get("text_embed")
+        te = te[0] if isinstance(te, tuple) else te
+        device = te.device if torch.is_tensor(te) else torch.device("cpu")
     gen = None
     if seed is not None:
         gen = torch.Generator(device=device)

@@ -82,3 +82,60 @@ def test_two_rank_sharded_run_equals_unsharded(tmp_path):
     # tests/test_parity_gpu.py::test_benchmark_size_properties checks the bitwise version of this on the GPU
     assert torch.allclose(sharded, single, rtol=0, atol=2e-5)
     assert not torch.allclose(sharded[0], sharded[1], atol=1e-2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# DiP: the broadcast object is the (BERT tokens, padding mask) pair; y['prefix'] is sharded with the batch
+CTX, PRED, MT = 6, 10, 5
+
+
+def _dip_sampler():
+    W = mo.OracleWeights(b200mdm.synthetic_state_dict(arch="trans_dec", num_layers=L, cond_dim=768, seed=6), L)
+    tabs = so.diffusion_tables(so.named_betas("cosine", STEPS))
+
+    def fn(model, shape, noise, model_kwargs, noise_tape, **kw):
+        y = model_kwargs["y"]
+        enc, tmask = y["text_embed"]
+        tape = [noise] + [noise_tape[k] for k in range(noise_tape.shape[0])]
+        return mo.sample_loop_dec(W, tabs, list(range(STEPS)), tape, enc, tmask, y["prefix"], y["scale"], y["lengths"])
+    return fn
+
+
+def _dip_inputs():
+    enc, tmask, prefix = b200mdm.synthetic_dip_inputs(B, MT, CTX, seed=9)
+    lengths = torch.tensor([10, 7, 10, 3, 9])
+    return dict(y=dict(text_embed=(enc, tmask), prefix=prefix, lengths=lengths, scale=torch.tensor([7.5, 1.0, 0.0, 4.0, 2.5]),
+                       mask=(torch.arange(PRED)[None] < lengths[:, None]).view(B, 1, 1, PRED)))
+
+
+def _dip_worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        kw = _dip_inputs()
+        if rank != 0:                       # only rank 0 ran the text tower
+            enc, tmask = kw["y"]["text_embed"]
+            kw["y"]["text_embed"] = (torch.zeros_like(enc), torch.ones_like(tmask))
+        out = parallel.sample_sharded(_dip_sampler(), None, (B, 263, 1, PRED), kw, n_steps=STEPS, noise_mode="global",
+                                      seed=78, device=torch.device("cpu"))
+        if rank == 0:
+            torch.save(out, out_path)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dip_two_rank_sharded_run_equals_unsharded(tmp_path):
+    kw = _dip_inputs()
+    s = parallel.shard_model_kwargs(kw, 1, 4)["y"]
+    assert s["text_embed"][0].shape == (MT, 3, 768) and s["text_embed"][1].shape == (3, MT) and s["prefix"].shape[0] == 3
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    out_path = str(tmp_path / "out.pt")
+    mp.spawn(_dip_worker, args=(2, port, out_path), nprocs=2, join=True)
+    sharded = torch.load(out_path)
+    single = parallel.sample_sharded(_dip_sampler(), None, (B, 263, 1, PRED), _dip_inputs(), n_steps=STEPS,
+                                     noise_mode="global", seed=78, device=torch.device("cpu"))
+    assert sharded.shape == (B, 263, 1, PRED)
+    assert torch.allclose(sharded, single, rtol=0, atol=5e-5)
