@@ -158,13 +158,11 @@ int b200mdm_test_gemm_f16(const void* a16_dev, const void* w16_dev, const float*
  * impl 0: tcgen05 kernel (S <= 256, the one the engine uses); impl 1: mma.sync kernel for longer sequences. */
 int b200mdm_test_attention(const void* qkv16_dev, void* out16_dev, const int32_t* kvlen_dev, int32_t n_samples,
                            int32_t S, int32_t d, int32_t impl, void* stream);
-/* h32[M,512] <- LayerNorm(h32 + A16[M,K] @ W16[512,K]^T + bias; gamma, beta, 1e-5) in place, h16 = fp16 copy
- * (the fused out-projection / FFN-down kernel of the encoder layer).  K % 8 == 0.
- * impl 0: column-split 2-CTA cluster, statistics through distributed shared memory (the one the engine uses);
- * impl 1: CTA-pair (cta_group::2) full-row variant. */
+/* h[M,512] <- LayerNorm(h + A16[M,K] @ W16[512,K]^T + bias; gamma, beta, 1e-5) in place (the fused out-projection /
+ * FFN-down kernel of the transformer layer).  h is the engine's residual-stream format: fp16 [M, 1024] = [hi | lo],
+ * value = hi + lo.  K % 8 == 0. */
 int b200mdm_test_gemm_resid_ln(const void* a16_dev, const void* w16_dev, const float* bias_dev, const float* gamma_dev,
-                               const float* beta_dev, float* h32_dev, void* h16_dev, int32_t M, int32_t K, int32_t impl,
-                               void* stream);
+                               const float* beta_dev, void* hres16_dev, int32_t M, int32_t K, void* stream);
 /* in-place LayerNorm over rows of h32 [M,512] + fp16 copy */
 int b200mdm_test_layernorm(float* h32_dev, void* h16_dev, const float* gamma_dev, const float* beta_dev, int32_t M,
                            void* stream);

@@ -71,7 +71,7 @@ def load():
     lib.b200mdm_launch_count.restype = i64
     lib.b200mdm_test_gemm_f16.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.b200mdm_test_attention.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
-    lib.b200mdm_test_gemm_resid_ln.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.b200mdm_test_gemm_resid_ln.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
     lib.b200mdm_test_layernorm.argtypes = [vp, vp, vp, vp, i32, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)

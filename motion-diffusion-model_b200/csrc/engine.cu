@@ -21,7 +21,6 @@
 #include "epilogues.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
-#include "gemm2_ln.cuh"
 #include "gemm_ln.cuh"
 #include "kernels.cuh"
 
@@ -99,6 +98,22 @@ static int make_map_3d(CUtensorMap* m, const void* ptr, uint64_t n, uint64_t row
   return B200MDM_OK;
 }
 
+// Residual stream fp16 [rows, 2d] = [hi | lo]: box {32 cols, 32 rows} with 64-byte rows and the 64-byte swizzle; an
+// epilogue chunk of 32 columns moves one such box from the hi half and one from the lo half.
+static int make_map_res(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t d) {
+  TRY(resolve_driver());
+  if (reinterpret_cast<uintptr_t>(ptr) & 15) return fail(B200MDM_EINVAL, "TMA operand misaligned");
+  cuuint64_t gdim[2] = {2 * d, rows};
+  cuuint64_t gstr[1] = {d * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200MDM_ECUDA, "cuTensorMapEncodeTiled(residual) failed (%d)", static_cast<int>(r));
+  return B200MDM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ engine
 struct Tensor32 {
   float* dev = nullptr;
@@ -115,7 +130,6 @@ struct LayerW {
   __half *wq_c = nullptr, *wkv_c = nullptr, *wo_c = nullptr;
   const float *bq_c = nullptr, *bkv_c = nullptr, *bo_c = nullptr, *g3 = nullptr, *be3 = nullptr;
   CUtensorMap m_wq_c, m_wkv_c, m_wo_c_256;
-  CUtensorMap m_wqkv_hi;   // first K columns only (layer 0 of the wide engine: the embedding GEMM writes no lo half)
 };
 
 struct GraphKey {
@@ -145,21 +159,21 @@ struct b200mdm_engine {
   int n_steps = 0;
   // per-(B,T) workspace
   int B = 0, T = 0, S = 0, halves = 1, Bp = 0, M = 0, MB = 0;
-  __half *xin16 = nullptr, *h16 = nullptr, *qkv16 = nullptr, *att16 = nullptr, *ffn16 = nullptr, *g16 = nullptr;
-  float *h32 = nullptr, *tok0 = nullptr, *condproj = nullptr, *proj = nullptr, *scale = nullptr, *x_work = nullptr;
+  __half *xin16 = nullptr, *hres = nullptr, *qkv16 = nullptr, *att16 = nullptr, *ffn16 = nullptr, *g16 = nullptr;
+  float *tok0 = nullptr, *condproj = nullptr, *proj = nullptr, *scale = nullptr, *x_work = nullptr;
   int *kvlen = nullptr, *tvec = nullptr, *action = nullptr;
   StepState* state = nullptr;
   CUtensorMap m_xin, m_h16, m_att, m_ffn, m_g16;      // A operands (loads, box 128 rows)
-  CUtensorMap m_qkv_st, m_ffn_st, m_h32_io, m_h16_st;            // epilogue slabs (box 32 rows x 128 bytes)
+  CUtensorMap m_qkv_st, m_ffn_st;                      // epilogue slabs (box 32 rows x 128 bytes)
+  CUtensorMap m_res;                                   // residual stream [hi | lo] (make_map_res)
   CUtensorMap m_att_q, m_att_kv, m_att_o;             // tcgen05 attention: per-sample 3-D views of qkv16 / att16
-  CUtensorMap m_h32_c, m_h32_u, m_h16_c, m_h16_u;      // per-CFG-half views of h32 / h16 for the embedding epilogue
+  CUtensorMap m_res_c, m_res_u;                        // per-CFG-half views of the residual stream (embedding epilogue)
   float* pe_bias = nullptr;
   bool cond_set = false;
   // trans_dec (DiP): prefix frames + text-token memory
   bool dec = false;
   int ctx = 0, s_off = 1, Mt = 0;
   int kw = 1;   // 2: fp16 activations between the layer GEMMs are [hi | lo] pairs along K (trans_dec engine)
-  CUtensorMap m_h16_hi;
   float *encperm = nullptr, *memtok = nullptr, *memproj = nullptr;   // [B*Mt, cond_dim], [B*Mt, d], [Bp*Mt, d]
   __half *mem16 = nullptr, *qc16 = nullptr, *kvc16 = nullptr;        // [Bp*Mt, d], [M, d], [Bp*Mt, 2d]
   unsigned char* memmask = nullptr;                                   // [Bp, Mt] 1 = padding
@@ -212,9 +226,7 @@ static int init_kernel_attrs() {
   TRY((set_gemm2_attr<EpiBiasF16<true>>()));
   TRY((set_gemm2_attr<EpiResidualF32>()));
   TRY((set_gemm2_attr<EpiBiasF16Wide<true>>()));
-  CUDA_TRY(cudaFuncSetAttribute(gemm_resid_ln_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLnSmem::TOTAL));
-  CUDA_TRY(cudaFuncSetAttribute(gemm_resid_ln_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLnSmem::TOTAL));
-  CUDA_TRY(cudaFuncSetAttribute(gemm2_resid_ln_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2LnSmem::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_resid_ln_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLnSmem::TOTAL));
   TRY((set_gemm_attr<128, EpiEmbed>()));
   TRY((set_gemm_attr<96, EpiOutStep>()));
   CUDA_TRY(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -284,29 +296,13 @@ static int launch_gemm2(const CUtensorMap& a, const CUtensorMap& b, const CUtens
 
 // h <- LayerNorm(h + A W^T + bias), 2-CTA cluster splitting the 512 columns, LayerNorm statistics exchanged through
 // distributed shared memory (w256: W map with box 256 rows)
-static int launch_gemm_resid_ln(const CUtensorMap& a, const CUtensorMap& w256, const CUtensorMap& h32_io, __half* h16, int M,
-                                int K, const float* bias, const float* gamma, const float* beta, cudaStream_t s,
-                                int num_sms, bool wide = false) {
+static int launch_gemm_resid_ln(const CUtensorMap& a, const CUtensorMap& w256, const CUtensorMap& res, int M, int K,
+                                const float* bias, const float* gamma, const float* beta, cudaStream_t s, int num_sms) {
   const int tiles = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int max_clusters = num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   GemmLnParams lp{bias, gamma, beta, 1e-5f};
-  CUDA_TRY(launch_k(wide ? gemm_resid_ln_cluster<true> : gemm_resid_ln_cluster<false>, dim3(2 * clusters), dim3(GLN_THREADS),
-                    GemmLnSmem::TOTAL, s, a, w256, h32_io, h16, M, K, lp));
-  return B200MDM_OK;
-}
-
-static long long* g_ln_trace = nullptr;   // debug: set through b200mdm_debug_trace()
-// h <- LayerNorm(h + A W^T + bias): residual + LayerNorm fused into the CTA-pair GEMM epilogue (N = 512)
-static int launch_gemm2_resid_ln(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& h32_io,
-                                 __half* h16, int M, int K, const float* bias, const float* gamma,
-                                 const float* beta, cudaStream_t s, int num_sms) {
-  const int tiles = (M + GEMM2_TILE_M - 1) / GEMM2_TILE_M;
-  const int max_clusters = num_sms / 2;
-  const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  LnParams lp{bias, gamma, beta, 1e-5f, g_ln_trace};
-  gemm2_resid_ln_tcgen05<<<2 * clusters, LN2_THREADS, Gemm2LnSmem::TOTAL, s>>>(a, w, h32_io, h16, M, K, lp);
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(launch_k(gemm_resid_ln_cluster, dim3(2 * clusters), dim3(GLN_THREADS), GemmLnSmem::TOTAL, s, a, w256, res, M, K, lp));
   return B200MDM_OK;
 }
 
@@ -399,8 +395,8 @@ extern "C" int b200mdm_create(const b200mdm_config* cfg, b200mdm_engine** out) {
 }
 
 static void free_workspace(b200mdm_engine* e) {
-  dfree(e->xin16); dfree(e->h16); dfree(e->qkv16); dfree(e->att16); dfree(e->ffn16); dfree(e->g16);
-  dfree(e->h32); dfree(e->tok0); dfree(e->condproj); dfree(e->proj); dfree(e->scale); dfree(e->x_work); dfree(e->pe_bias);
+  dfree(e->xin16); dfree(e->hres); dfree(e->qkv16); dfree(e->att16); dfree(e->ffn16); dfree(e->g16);
+  dfree(e->tok0); dfree(e->condproj); dfree(e->proj); dfree(e->scale); dfree(e->x_work); dfree(e->pe_bias);
   dfree(e->kvlen); dfree(e->tvec); dfree(e->action);
   dfree(e->encperm); dfree(e->memtok); dfree(e->memproj); dfree(e->mem16); dfree(e->qc16); dfree(e->kvc16); dfree(e->memmask);
   e->Mt = 0; e->prefix_set = false;
@@ -565,7 +561,6 @@ extern "C" int b200mdm_finalize_weights(b200mdm_engine* e, void* stream) {
     TRY(to_f16_k(w1, &w.w1, ff, d, kw, s));
     TRY(to_f16_k(w2, &w.w2, d, ff, kw, s));
     TRY(make_map(&w.m_wqkv, w.wqkv, 3 * d, kw * d, kw * d, 128));
-    TRY(make_map(&w.m_wqkv_hi, w.wqkv, 3 * d, d, kw * d, 128));
     TRY(make_map(&w.m_wo, w.wo, d, kw * d, kw * d, 128));
     TRY(make_map(&w.m_w1, w.w1, ff, kw * d, kw * d, 128));
     TRY(make_map(&w.m_w2, w.w2, d, kw * ff, kw * ff, 128));
@@ -634,8 +629,7 @@ static int build_workspace(b200mdm_engine* e, int B, int T, int halves) {
   const size_t M = static_cast<size_t>(Bp) * S, MB = static_cast<size_t>(B) * S;
   TRY(dalloc(&e->xin16, MB * 3 * e->Kp_in, true));
   const int kw = e->kw;
-  TRY(dalloc(&e->h16, M * d * kw, true));
-  TRY(dalloc(&e->h32, M * d));
+  TRY(dalloc(&e->hres, M * d * 2, true));   // residual stream, fp16 [hi | lo]
   TRY(dalloc(&e->qkv16, M * 3 * d));
   TRY(dalloc(&e->att16, M * d * kw));
   TRY(dalloc(&e->ffn16, M * e->ff * kw));
@@ -663,12 +657,12 @@ static int build_workspace(b200mdm_engine* e, int B, int T, int halves) {
     cudaDeviceProp prop;
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
-      const size_t want = M * d * sizeof(float);
+      const size_t want = M * d * 2 * sizeof(__half);
       const size_t carve = want < static_cast<size_t>(prop.persistingL2CacheMaxSize) ? want : static_cast<size_t>(prop.persistingL2CacheMaxSize);
       cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
       cudaStreamAttrValue attr;
       memset(&attr, 0, sizeof(attr));
-      attr.accessPolicyWindow.base_ptr = e->h32;
+      attr.accessPolicyWindow.base_ptr = e->hres;
       attr.accessPolicyWindow.num_bytes = want < static_cast<size_t>(prop.accessPolicyMaxWindowSize) ? want : static_cast<size_t>(prop.accessPolicyMaxWindowSize);
       attr.accessPolicyWindow.hitRatio = want <= carve ? 1.0f : static_cast<float>(carve) / static_cast<float>(want);
       attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
@@ -678,24 +672,21 @@ static int build_workspace(b200mdm_engine* e, int B, int T, int halves) {
     }
   }
   TRY(make_map(&e->m_xin, e->xin16, MB, 3 * e->Kp_in, 3 * e->Kp_in, GEMM_BLOCK_M));
-  TRY(make_map(&e->m_h16, e->h16, M, kw * d, kw * d, GEMM_BLOCK_M));
-  TRY(make_map(&e->m_h16_hi, e->h16, M, d, kw * d, GEMM_BLOCK_M));
+  // GEMM A operand = the hi half of the residual stream (kw = 2, trans_dec: both halves, K = 2d against [W | W])
+  TRY(make_map(&e->m_h16, e->hres, M, kw * d, 2 * d, GEMM_BLOCK_M));
   TRY(make_map(&e->m_att, e->att16, M, kw * d, kw * d, GEMM_BLOCK_M));
   TRY(make_map(&e->m_ffn, e->ffn16, M, kw * e->ff, kw * e->ff, GEMM_BLOCK_M));
   TRY(make_map(&e->m_g16, e->g16, MB, 3 * d, 3 * d, GEMM_BLOCK_M));
   TRY(make_map_t(&e->m_qkv_st, e->qkv16, 2, M, 3 * d, 3 * d, 32));
   TRY(make_map_t(&e->m_ffn_st, e->ffn16, 2, M, kw * e->ff, kw * e->ff, 32));
-  TRY(make_map_t(&e->m_h32_io, e->h32, 4, M, d, d, 32));
-  TRY(make_map_t(&e->m_h16_st, e->h16, 2, M, d, kw * d, 32));
+  TRY(make_map_res(&e->m_res, e->hres, M, d));
   if (S <= ATC_MAX_KEYS) {
     AttnMaps am;
     TRY(make_attn_maps(&am, e->qkv16, e->att16, Bp, S, d, kw));
     e->m_att_q = am.q; e->m_att_kv = am.kv; e->m_att_o = am.o;
   }
-  TRY(make_map_t(&e->m_h32_c, e->h32, 4, MB, d, d, 32));
-  TRY(make_map_t(&e->m_h16_c, e->h16, 2, MB, d, kw * d, 32));
-  TRY(make_map_t(&e->m_h32_u, e->h32 + (halves == 2 ? MB * d : 0), 4, MB, d, d, 32));
-  TRY(make_map_t(&e->m_h16_u, e->h16 + (halves == 2 ? MB * d * kw : 0), 2, MB, d, kw * d, 32));
+  TRY(make_map_res(&e->m_res_c, e->hres, MB, d));
+  TRY(make_map_res(&e->m_res_u, e->hres + (halves == 2 ? MB * d * 2 : 0), MB, d));
   TRY(dalloc(&e->pe_bias, static_cast<size_t>(S) * d));
   pe_bias_kernel<<<S, 128>>>(e->pe_bias, e->pe, e->b_in, S, d);
   CUDA_TRY(cudaGetLastError());
@@ -868,14 +859,14 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
   }
   {
     EpiEmbed::Params p;
-    p.h32_c = e->m_h32_c; p.h32_u = e->m_h32_u; p.h16_c = e->m_h16_c; p.h16_u = e->m_h16_u;
+    p.res_c = e->m_res_c; p.res_u = e->m_res_u;
     p.pe_bias = e->pe_bias;
     p.S = S; p.d = d; p.halves = e->halves;
     TRY((launch_gemm<128, EpiEmbed>(e->m_xin, e->m_win, e->m_xin, e->MB, d, 3 * Kp, p, s, e->num_sms)));
     ++nk;
   }
   if (!e->dec) {
-    CUDA_TRY(launch_k(tok0_rows_kernel, dim3(e->Bp), dim3(128), 0, s, e->h32, e->h16, e->condproj, e->temb_table, e->pe,
+    CUDA_TRY(launch_k(tok0_rows_kernel, dim3(e->Bp), dim3(128), 0, s, e->hres, e->condproj, e->temb_table, e->pe,
                       a.explicit_t ? e->tvec : nullptr, e->tmap, e->state, B, S, d, e->cfg.temb_rows));
   } else {
     // cross-attention memory of this step: text tokens + timestep embedding (model/mdm.py:218-220)
@@ -888,11 +879,8 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
   for (int l = 0; l < e->L; ++l) {
     const LayerW& w = e->layers[l];
     {
-      // wide engine, layer 0: the embedding GEMM leaves only the hi half of h16 -> K = d over the first half of [W | W]
-      const bool hi_only = wide && l == 0;
       EpiBiasF16<false>::Params p{w.bqkv};
-      TRY((launch_gemm2<EpiBiasF16<false>>(hi_only ? e->m_h16_hi : e->m_h16, hi_only ? w.m_wqkv_hi : w.m_wqkv, e->m_qkv_st, e->M,
-                                           3 * d, hi_only ? d : kw * d, p, s, e->num_sms)));
+      TRY((launch_gemm2<EpiBiasF16<false>>(e->m_h16, w.m_wqkv, e->m_qkv_st, e->M, 3 * d, kw * d, p, s, e->num_sms)));
     }
     if (S <= ATC_MAX_KEYS) {
       AttnMaps am{e->m_att_q, e->m_att_kv, e->m_att_o};
@@ -901,7 +889,7 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
       if (wide) return fail(B200MDM_ENOTIMPL, "trans_dec sequences longer than %d tokens", ATC_MAX_KEYS);
       TRY(launch_attention_mma(e->qkv16, e->att16, e->kvlen, e->Bp, S, d, e->H, s));
     }
-    TRY(launch_gemm_resid_ln(e->m_att, w.m_wo_256, e->m_h32_io, e->h16, e->M, kw * d, w.bo, w.g1, w.be1, s, e->num_sms, wide));
+    TRY(launch_gemm_resid_ln(e->m_att, w.m_wo_256, e->m_res, e->M, kw * d, w.bo, w.g1, w.be1, s, e->num_sms));
     if (e->dec) {
       // cross-attention block of nn.TransformerDecoderLayer: q from the sequence, k/v from the text memory
       {
@@ -914,7 +902,7 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
       }
       CUDA_TRY(launch_k(cross_attention_kernel, dim3(e->H, e->Bp), dim3(128), static_cast<size_t>(e->Mt) * 512, s, e->qc16,
                         e->kvc16, e->memmask, e->att16, S, e->Mt, d, 1.0f / sqrtf(128.0f)));
-      TRY(launch_gemm_resid_ln(e->m_att, w.m_wo_c_256, e->m_h32_io, e->h16, e->M, kw * d, w.bo_c, w.g2, w.be2, s, e->num_sms, wide));
+      TRY(launch_gemm_resid_ln(e->m_att, w.m_wo_c_256, e->m_res, e->M, kw * d, w.bo_c, w.g2, w.be2, s, e->num_sms));
       nk += 4;
     }
     if (wide) {
@@ -924,11 +912,11 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
       EpiBiasF16<true>::Params p{w.b1};
       TRY((launch_gemm2<EpiBiasF16<true>>(e->m_h16, w.m_w1, e->m_ffn_st, e->M, ff, d, p, s, e->num_sms)));
     }
-    TRY(launch_gemm_resid_ln(e->m_ffn, w.m_w2_256, e->m_h32_io, e->h16, e->M, kw * ff, w.b2, e->dec ? w.g3 : w.g2,
-                             e->dec ? w.be3 : w.be2, s, e->num_sms, wide));
+    TRY(launch_gemm_resid_ln(e->m_ffn, w.m_w2_256, e->m_res, e->M, kw * ff, w.b2, e->dec ? w.g3 : w.g2,
+                             e->dec ? w.be3 : w.be2, s, e->num_sms));
     nk += 5;
   }
-  CUDA_TRY(launch_k(blend_split_kernel, dim3((e->MB + 7) / 8), dim3(256), 0, s, e->h32, e->g16, e->scale, B, S, d, e->halves));
+  CUDA_TRY(launch_k(blend_split_kernel, dim3((e->MB + 7) / 8), dim3(256), 0, s, e->hres, e->g16, e->scale, B, S, d, e->halves));
   ++nk;
   {
     EpiOutStep::Params p;
@@ -1165,31 +1153,24 @@ extern "C" int b200mdm_test_attention(const void* qkv16_dev, void* out16_dev, co
 }
 
 extern "C" int b200mdm_test_gemm_resid_ln(const void* a16_dev, const void* w16_dev, const float* bias_dev,
-                                          const float* gamma_dev, const float* beta_dev, float* h32_dev, void* h16_dev,
-                                          int32_t M, int32_t K, int32_t impl, void* stream) {
-  if (!a16_dev || !w16_dev || !bias_dev || !gamma_dev || !beta_dev || !h32_dev || !h16_dev || M <= 0 || K <= 0 || K % 8)
+                                          const float* gamma_dev, const float* beta_dev, void* hres16_dev, int32_t M,
+                                          int32_t K, void* stream) {
+  if (!a16_dev || !w16_dev || !bias_dev || !gamma_dev || !beta_dev || !hres16_dev || M <= 0 || K <= 0 || K % 8)
     return fail(B200MDM_EINVAL, "bad argument");
   TRY(init_kernel_attrs());
   int dev = 0, sms = 148;
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  CUtensorMap ma, mb, m32;
+  CUtensorMap ma, mb, mr;
   TRY(make_map(&ma, a16_dev, M, K, K, GEMM_BLOCK_M));
-  if (impl == 0) {
-    TRY(make_map(&mb, w16_dev, LN_D, K, K, 256));
-    TRY(make_map_t(&m32, h32_dev, 4, M, LN_D, LN_D, 32));
-    return launch_gemm_resid_ln(ma, mb, m32, static_cast<__half*>(h16_dev), M, K, bias_dev, gamma_dev, beta_dev,
-                                static_cast<cudaStream_t>(stream), sms);
-  }
-  TRY(make_map(&mb, w16_dev, LN_D, K, K, 128));
-  TRY(make_map_t(&m32, h32_dev, 4, M, LN_D, LN_D, 32));
-  return launch_gemm2_resid_ln(ma, mb, m32, static_cast<__half*>(h16_dev), M, K, bias_dev, gamma_dev, beta_dev, static_cast<cudaStream_t>(stream), sms);
+  TRY(make_map(&mb, w16_dev, GLN_D, K, K, 256));
+  TRY(make_map_res(&mr, hres16_dev, M, GLN_D));
+  return launch_gemm_resid_ln(ma, mb, mr, M, K, bias_dev, gamma_dev, beta_dev, static_cast<cudaStream_t>(stream), sms);
 }
 
 // Debug aid (not part of the public header): device buffer of 32 int64 that receives clock64 stamps of the fused
 // residual+LayerNorm kernel (block 0, first epilogue warp): tile start, accumulator ready, pass 1 done, stats done, pass 2 done.
 extern "C" int b200mdm_debug_trace(long long* dev_buf) {
-  g_ln_trace = dev_buf;
   CUDA_TRY(cudaMemcpyToSymbol(g_gemm2_trace, &dev_buf, sizeof(dev_buf)));
   return B200MDM_OK;
 }

@@ -16,6 +16,32 @@ namespace b200 {
 
 // byte offset of 16-byte chunk j (0..7) of row r inside a [32 x 128 B] slab with the TMA SWIZZLE_128B pattern
 __device__ __forceinline__ uint32_t slab_off(int r, int j) { return r * 128 + ((j ^ (r & 7)) << 4); }
+// byte offset of 16-byte chunk j (0..3) of row r inside a [32 x 64 B] half-slab with the TMA SWIZZLE_64B pattern
+// (address bits 4-5 xor bits 7-8).  A residual-stream slab is two of these: hi halves at +0, lo halves at +2048.
+__device__ __forceinline__ uint32_t slab64_off(int r, int j) { return r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
+
+// 8 fp32 values -> 4 packed half2 "hi" words + 4 packed half2 "lo" words with hi + lo = v to ~22 bits
+__device__ __forceinline__ void split_hi_lo8(const float (&v)[8], uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+    lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+}
+// the inverse for one 16-byte group of hi and one of lo: 8 fp32 values
+__device__ __forceinline__ void join_hi_lo8(const uint4& h, const uint4& l, float (&v)[8]) {
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
+    v[2 * i] = a.x + b.x;
+    v[2 * i + 1] = a.y + b.y;
+  }
+}
 
 // exact (erf) GELU, torch F.gelu default (reference model/mdm.py:80 activation="gelu"):  gelu(x) = x * Phi(x).
 // Phi(-t) = 2^q(t) with q a degree-6 minimax fit of log2(0.5*erfc(t/sqrt 2)) on [0, 5.5] (|Phi error| < 1.5e-7,
@@ -261,50 +287,45 @@ struct EpiResidualF32 {
 //   conditioning token, mdm.py:251) is produced by tok0_rows_kernel right after this GEMM.
 //   Outputs: h32 (fp32 residual stream) and h16 (fp16 copy = next GEMM's A operand).
 struct EpiEmbed {
-  static constexpr int SMEM_PER_WARP = 4 * 4096;  // 2 fp32 slabs + 2 fp16 slabs
+  static constexpr int SMEM_PER_WARP = 2 * 4096;  // two [hi | lo] slabs
   static constexpr bool RELEASE_EARLY = true;
   template <class P> static __device__ __forceinline__ void preload(const P&, float*, int, int, int) {}
   struct Params {
-    CUtensorMap h32_c, h32_u, h16_c, h16_u;  // [B*S, d] views of the two halves, box 32 rows x 128 bytes
+    CUtensorMap res_c, res_u;                 // residual stream [rows, 2d] = [hi | lo] of the two CFG halves,
+                                              // box {32 cols, 32 rows} (64-byte rows, SWIZZLE_64B)
     const float* pe_bias;                     // [S, d] = pe[s] + bias
     int S, d, halves;
   };
   static __device__ __forceinline__ void tile_begin(EpiCtx&, const Params&, int, int) {}
   static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0,
                                                int) {
-    const int half = (col0 >> 5) & 1;
-    uint8_t* s32 = ctx.smem + (ctx.seq & 1) * 4096;
-    uint8_t* s16 = ctx.smem + 8192 + ((ctx.seq >> 1) & 1) * 4096;
-    if (ctx.lane == 0) bulk_wait_group_read<1>();  // every group older than the previous chunk's has been read
+    uint8_t* slab = ctx.smem + (ctx.seq & 1) * 4096;
+    if (ctx.lane == 0) bulk_wait_group_read<1>();  // the group that last read this slab (two chunks ago) is done
     __syncwarp();
     const int row = row0 + ctx.lane;
     const int s = (row < ctx.M) ? row % p.S : 0;
     const float* pb = p.pe_bias + static_cast<size_t>(s) * p.d + col0;
-    uint32_t pk[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(pb + 4 * j));
-      float4 o;
-      o.x = __uint_as_float(raw[4 * j + 0]) + a.x;
-      o.y = __uint_as_float(raw[4 * j + 1]) + a.y;
-      o.z = __uint_as_float(raw[4 * j + 2]) + a.z;
-      o.w = __uint_as_float(raw[4 * j + 3]) + a.w;
-      *reinterpret_cast<float4*>(s32 + slab_off(ctx.lane, j)) = o;
-      pk[2 * j] = pack_half2(o.x, o.y);
-      pk[2 * j + 1] = pack_half2(o.z, o.w);
+    for (int j = 0; j < 4; ++j) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(pb + 8 * j));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(pb + 8 * j + 4));
+      const float o[8] = {__uint_as_float(raw[8 * j + 0]) + a0.x, __uint_as_float(raw[8 * j + 1]) + a0.y,
+                          __uint_as_float(raw[8 * j + 2]) + a0.z, __uint_as_float(raw[8 * j + 3]) + a0.w,
+                          __uint_as_float(raw[8 * j + 4]) + a1.x, __uint_as_float(raw[8 * j + 5]) + a1.y,
+                          __uint_as_float(raw[8 * j + 6]) + a1.z, __uint_as_float(raw[8 * j + 7]) + a1.w};
+      uint32_t hi[4], lo[4];
+      split_hi_lo8(o, hi, lo);
+      *reinterpret_cast<uint4*>(slab + slab64_off(ctx.lane, j)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(slab + 2048 + slab64_off(ctx.lane, j)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      *reinterpret_cast<uint4*>(s16 + slab_off(ctx.lane, half * 4 + j)) =
-          make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
     fence_proxy_async_smem();
     __syncwarp();
     if (ctx.lane == 0) {
-      tma_store_2d(&p.h32_c, s32, col0, row0);
-      if (p.halves == 2) tma_store_2d(&p.h32_u, s32, col0, row0);
-      if (half == 1) {
-        tma_store_2d(&p.h16_c, s16, col0 - 32, row0);
-        if (p.halves == 2) tma_store_2d(&p.h16_u, s16, col0 - 32, row0);
+      tma_store_2d(&p.res_c, slab, col0, row0);
+      tma_store_2d(&p.res_c, slab + 2048, p.d + col0, row0);
+      if (p.halves == 2) {
+        tma_store_2d(&p.res_u, slab, col0, row0);
+        tma_store_2d(&p.res_u, slab + 2048, p.d + col0, row0);
       }
       bulk_commit_group();
     }

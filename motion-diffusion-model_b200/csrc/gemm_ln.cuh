@@ -1,6 +1,6 @@
 // tcgen05 GEMM with residual add + LayerNorm fused into the epilogue, N = d_model = 512 split over a 2-CTA cluster:
 //
-//     h <- LayerNorm( h + A W^T + bias ; gamma, beta, eps )        in place on h32 (fp32) + fp16 copy h16
+//     h <- LayerNorm( h + A W^T + bias ; gamma, beta, eps )        in place on the residual stream (fp16 [hi | lo])
 //     (post-norm nn.TransformerEncoderLayer of the reference, built at model/mdm.py:77-84)
 //
 // Both CTAs of a cluster work on the SAME 128 rows; CTA r owns columns [256 r, 256 r + 256) (its own 256 rows of W,
@@ -14,8 +14,9 @@
 //   exchange  partials of the two parts meet in shared memory (named barrier); the part-0 warp pushes the CTA's partial
 //             into the PEER CTA's shared memory (st.shared::cluster) and signals the peer's mbarrier; both CTAs now own
 //             the statistics of the complete 512-wide rows
-//   pass 2    y = (v - mean) rstd gamma + beta -> fp32 slab -> TMA store (h32) ; fp16 -> 256-bit st.global (h16)
-// (measured: TMA slabs for the fp32 stream beat direct 256-bit loads/stores, 43.8 / 51.8 us vs 52.0 / 59.7 us per launch)
+//   pass 2    y = (v - mean) rstd gamma + beta -> [hi | lo] fp16 slab -> TMA store
+// History (profiles/): an fp32 stream + separate fp16 copy cost 6 B/element of stores and 41.6 / 49.2 us per launch;
+// TMA slabs beat direct 256-bit loads/stores (43.8 / 51.8 us vs 52.0 / 59.7 us).
 #pragma once
 #include "epilogues.cuh"
 #include "gemm.cuh"
@@ -48,13 +49,14 @@ struct GemmLnParams {
 };
 
 // map_a: A [M, K] fp16, box 128 rows; map_b: W [512, K] fp16, box 256 rows; map_h32: h32 [M, 512] fp32, box 32 x 32
-// (loaded and stored in place); h16 [M, 512] fp16 -- or, WIDE, [M, 1024] = [hi | lo] (trans_dec engine: the next GEMM
-// runs over K = 1024 against [W | W], which keeps the normalised activations to ~22 bits)
-template <bool WIDE>
+// map_res: the residual stream h, fp16 [M, 1024] = [hi | lo] (hi + lo carries ~22 bits), box {32 cols, 32 rows} with
+// 64-byte rows (SWIZZLE_64B): a 4 KB slab = the hi half-slab of 32 columns + the lo half-slab.  Loaded and stored in place.
+// The hi half doubles as the fp16 A operand of the next GEMM (the trans_dec engine feeds both halves, K = 1024).
+// Versus an fp32 stream + fp16 copy this writes 4 instead of 6 bytes per element: the epilogue is bound by the SM's
+// store bandwidth (measured ~13 B/clk/SM), not by the MMAs.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GLN_THREADS, 1)
 gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      const __grid_constant__ CUtensorMap map_h32, __half* __restrict__ h16, int M, int K,
-                      const GemmLnParams lp) {
+                      const __grid_constant__ CUtensorMap map_res, int M, int K, const GemmLnParams lp) {
   using SM = GemmLnSmem;
   constexpr int STAGES = SM::STAGES;
 
@@ -97,7 +99,7 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
-    tma_prefetch_desc(&map_h32);
+    tma_prefetch_desc(&map_res);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -189,7 +191,8 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (lane == 0) {
           bulk_wait_group_read<0>();                  // stores out of these slabs (previous tile, pass 2) have been read
           mbar_expect_tx(&rb[seq & 1], 4096);
-          tma_load_2d(slab[seq & 1], &map_h32, &rb[seq & 1], gcol + 32 * c, row0);
+          tma_load_2d(slab[seq & 1], &map_res, &rb[seq & 1], gcol + 32 * c, row0);
+          tma_load_2d(slab[seq & 1] + 2048, &map_res, &rb[seq & 1], GLN_D + gcol + 32 * c, row0);
         }
       };
       if (live) {
@@ -213,19 +216,20 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
           tmem_ld_wait();
           const uint8_t* sl = slab[rseq & 1];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 r = *reinterpret_cast<const float4*>(sl + slab_off(lane, j));
-            const float4 b = *reinterpret_cast<const float4*>(bias_s + 32 * c + 4 * j);
-            const float v0 = r.x + (__uint_as_float(raw[4 * j + 0]) + b.x);
-            const float v1 = r.y + (__uint_as_float(raw[4 * j + 1]) + b.y);
-            const float v2 = r.z + (__uint_as_float(raw[4 * j + 2]) + b.z);
-            const float v3 = r.w + (__uint_as_float(raw[4 * j + 3]) + b.w);
-            sum += (v0 + v1) + (v2 + v3);
-            sumsq = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, sumsq))));
-            raw[4 * j + 0] = __float_as_uint(v0);
-            raw[4 * j + 1] = __float_as_uint(v1);
-            raw[4 * j + 2] = __float_as_uint(v2);
-            raw[4 * j + 3] = __float_as_uint(v3);
+          for (int j = 0; j < 4; ++j) {   // 8 columns: 16 bytes of hi + 16 bytes of lo
+            float r[8];
+            join_hi_lo8(*reinterpret_cast<const uint4*>(sl + slab64_off(lane, j)),
+                        *reinterpret_cast<const uint4*>(sl + 2048 + slab64_off(lane, j)), r);
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + 32 * c + 8 * j);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 32 * c + 8 * j + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float v = r[i] + (__uint_as_float(raw[8 * j + i]) + bb[i]);
+              sum += v;
+              sumsq = fmaf(v, v, sumsq);
+              raw[8 * j + i] = __float_as_uint(v);
+            }
           }
           tmem_st_32x32(taddr + 32 * c, raw);
           __syncwarp();
@@ -265,40 +269,27 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
             if (lane == 0) bulk_wait_group_read<1>();
             __syncwarp();
           }
-          uint32_t pk[16];
-          uint32_t pl[WIDE ? 16 : 1];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 g = *reinterpret_cast<const float4*>(gamma_s + 32 * c + 4 * j);
-            const float4 be = *reinterpret_cast<const float4*>(beta_s + 32 * c + 4 * j);
-            float4 y;
-            y.x = (__uint_as_float(raw[4 * j + 0]) - mean) * rstd * g.x + be.x;
-            y.y = (__uint_as_float(raw[4 * j + 1]) - mean) * rstd * g.y + be.y;
-            y.z = (__uint_as_float(raw[4 * j + 2]) - mean) * rstd * g.z + be.z;
-            y.w = (__uint_as_float(raw[4 * j + 3]) - mean) * rstd * g.w + be.w;
-            *reinterpret_cast<float4*>(o32 + slab_off(lane, j)) = y;
-            pk[2 * j] = pack_half2(y.x, y.y);
-            pk[2 * j + 1] = pack_half2(y.z, y.w);
-            if (WIDE) {
-              const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&pk[2 * j]));
-              const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&pk[2 * j + 1]));
-              pl[2 * j] = pack_half2(y.x - f0.x, y.y - f0.y);
-              pl[2 * j + 1] = pack_half2(y.z - f1.x, y.w - f1.y);
-            }
-          }
-          if (row0 + lane < M) {   // fp16 copy: 64 contiguous bytes of this thread's row, two whole 32-byte sectors
-            __half* dst = h16 + static_cast<size_t>(row0 + lane) * (WIDE ? 2 * GLN_D : GLN_D) + gcol + 32 * c;
-            stg256(dst, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
-            stg256(dst + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
-            if (WIDE) {
-              stg256(dst + GLN_D, pl[0], pl[1], pl[2], pl[3], pl[4], pl[5], pl[6], pl[7]);
-              stg256(dst + GLN_D + 16, pl[8], pl[9], pl[10], pl[11], pl[12], pl[13], pl[14], pl[15]);
-            }
+          for (int j = 0; j < 4; ++j) {
+            const float4 g0 = *reinterpret_cast<const float4*>(gamma_s + 32 * c + 8 * j);
+            const float4 g1 = *reinterpret_cast<const float4*>(gamma_s + 32 * c + 8 * j + 4);
+            const float4 e0 = *reinterpret_cast<const float4*>(beta_s + 32 * c + 8 * j);
+            const float4 e1 = *reinterpret_cast<const float4*>(beta_s + 32 * c + 8 * j + 4);
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+            float y[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] = (__uint_as_float(raw[8 * j + i]) - mean) * rstd * gg[i] + ee[i];
+            uint32_t hi[4], lo[4];
+            split_hi_lo8(y, hi, lo);
+            *reinterpret_cast<uint4*>(o32 + slab64_off(lane, j)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(o32 + 2048 + slab64_off(lane, j)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&map_h32, o32, gcol + 32 * c, row0);
+            tma_store_2d(&map_res, o32, gcol + 32 * c, row0);
+            tma_store_2d(&map_res, o32 + 2048, GLN_D + gcol + 32 * c, row0);
             bulk_commit_group();
           }
           if (tr) tr[tri++] = clock64();

@@ -44,7 +44,8 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __half* __restric
 //   h[b', s=0, :] = (condproj[b', :] + temb_table[t(b'), :]) + pe[0, :]
 //   t(b') = tvec[b' % B] when tvec != nullptr (model called with explicit timesteps), else timestep_map[state->cur]
 // Runs right after the embedding GEMM (which leaves placeholder values in these rows).
-__global__ void tok0_rows_kernel(float* __restrict__ h32, __half* __restrict__ h16, const float* __restrict__ condproj,
+// The residual stream is an fp16 [hi | lo] pair per element (row = 2d halves, hi + lo carries ~22 bits).
+__global__ void tok0_rows_kernel(__half* __restrict__ hres, const float* __restrict__ condproj,
                                  const float* __restrict__ temb_table, const float* __restrict__ pe,
                                  const int* __restrict__ tvec, const int* __restrict__ tmap,
                                  const StepState* __restrict__ state, int B, int S, int d, int temb_rows) {
@@ -56,8 +57,9 @@ __global__ void tok0_rows_kernel(float* __restrict__ h32, __half* __restrict__ h
   const size_t row = static_cast<size_t>(bp) * S;
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     const float v = (condproj[static_cast<size_t>(bp) * d + c] + temb_table[static_cast<size_t>(t) * d + c]) + pe[c];
-    h32[row * d + c] = v;
-    h16[row * d + c] = __float2half_rn(v);
+    const __half hi = __float2half_rn(v);
+    hres[row * 2 * d + c] = hi;
+    hres[row * 2 * d + d + c] = __float2half_rn(v - __half2float(hi));
   }
 }
 
@@ -132,7 +134,7 @@ __global__ void layernorm512_kernel(float* __restrict__ h32, __half* __restrict_
 //   v = h_u + scale[b] * (h_c - h_u)   (same expression as utils/sampler_util.py:34, applied before the linear
 //   OutputProcess: W(h_u + s(h_c-h_u)) + b == out_u + s(out_c - out_u) exactly in real arithmetic)
 //   halves == 1: v = h.       g16 row layout: [hi | lo | hi], ld = 3*d.
-__global__ void blend_split_kernel(const float* __restrict__ h32, __half* __restrict__ g16,
+__global__ void blend_split_kernel(const __half* __restrict__ hres, __half* __restrict__ g16,
                                    const float* __restrict__ scale, int B, int S, int d, int halves) {
   pdl_launch_dependents();
   pdl_wait();
@@ -140,14 +142,18 @@ __global__ void blend_split_kernel(const float* __restrict__ h32, __half* __rest
   const int lane = threadIdx.x & 31;
   if (row >= B * S) return;
   const int b = row / S;
-  const float* hc = h32 + static_cast<size_t>(row) * d;
-  const float* hu = h32 + (static_cast<size_t>(B) * S + row) * d;
+  const __half* hc = hres + static_cast<size_t>(row) * 2 * d;                         // [hi | lo] rows
+  const __half* hu = hres + (static_cast<size_t>(B) * S + row) * 2 * d;
   const float sc = (halves == 2) ? scale[b] : 0.f;
   __half* dst = g16 + static_cast<size_t>(row) * 3 * d;
   for (int c = lane * 2; c < d; c += 64) {
-    float2 a = *reinterpret_cast<const float2*>(hc + c);
+    const float2 ah = __half22float2(*reinterpret_cast<const __half2*>(hc + c));
+    const float2 al = __half22float2(*reinterpret_cast<const __half2*>(hc + d + c));
+    float2 a = make_float2(ah.x + al.x, ah.y + al.y);
     if (halves == 2) {
-      const float2 u = *reinterpret_cast<const float2*>(hu + c);
+      const float2 uh = __half22float2(*reinterpret_cast<const __half2*>(hu + c));
+      const float2 ul = __half22float2(*reinterpret_cast<const __half2*>(hu + d + c));
+      const float2 u = make_float2(uh.x + ul.x, uh.y + ul.y);
       a.x = __fadd_rn(u.x, __fmul_rn(sc, __fsub_rn(a.x, u.x)));
       a.y = __fadd_rn(u.y, __fmul_rn(sc, __fsub_rn(a.y, u.y)));
     }

@@ -10,8 +10,8 @@ lib.b200mdm_debug_trace.argtypes = [ctypes.c_void_p]
 for K in (512, 1024):
     a = torch.randn(M, K, device="cuda").half(); w = (torch.randn(512, K, device="cuda") / K ** 0.5).half()
     b = torch.randn(512, device="cuda"); g = torch.ones(512, device="cuda"); be = torch.zeros(512, device="cuda")
-    h32 = torch.randn(M, 512, device="cuda"); h16 = torch.empty(M, 512, device="cuda", dtype=torch.float16)
-    call = lambda: _lib.check(lib.b200mdm_test_gemm_resid_ln(a.data_ptr(), w.data_ptr(), b.data_ptr(), g.data_ptr(), be.data_ptr(), h32.data_ptr(), h16.data_ptr(), M, K, 0, st))
+    hres = torch.randn(M, 1024, device="cuda").half(); hres[:, 512:] *= 1e-3
+    call = lambda: _lib.check(lib.b200mdm_test_gemm_resid_ln(a.data_ptr(), w.data_ptr(), b.data_ptr(), g.data_ptr(), be.data_ptr(), hres.data_ptr(), M, K, st))
     for _ in range(3): call()
     torch.cuda.synchronize()
     buf.zero_(); lib.b200mdm_debug_trace(buf.data_ptr()); call(); torch.cuda.synchronize(); lib.b200mdm_debug_trace(None)
