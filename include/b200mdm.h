@@ -149,6 +149,17 @@ int b200mdm_q_sample(b200mdm_engine* e, float sqrt_ac, float sqrt_1mac, const fl
 /* Kernels launched by this engine since creation / since the last reset (bench.py's gpu_launches). */
 int64_t b200mdm_launch_count(b200mdm_engine* e, int32_t reset);
 
+/* ---- post-loop step: sample/generate.py:161-166 for data_rep 'hml_vec' -- inv_transform
+ * (data * std + mean, data_loaders/humanml/data/dataset.py:309-310) + recover_from_ric (data_loaders/humanml/scripts/
+ * motion_process.py:366-385,437-452) in one kernel, any input / output layout through element strides:
+ *   data element (b, feature f, frame t)       at data_dev[b*stride_b + f*stride_f + t*stride_t]
+ *   out  element (b, frame t, joint j, axis c) at out_dev[b*ostride_b + t*ostride_t + (3j + c)*ostride_c]
+ * mean_dev / std_dev: fp32 [features] or both NULL (input already de-normalised).  njoints 22 (263 features) / 21 (251). */
+int b200mdm_recover_from_ric(const float* data_dev, int64_t stride_b, int64_t stride_f, int64_t stride_t,
+                             const float* mean_dev, const float* std_dev, float* out_dev, int64_t ostride_b,
+                             int64_t ostride_t, int64_t ostride_c, int32_t batch, int32_t nframes, int32_t njoints,
+                             void* stream);
+
 /* ---- kernel-level entry points (used by tests/ to check each kernel against a torch fp32 restatement) ---- */
 /* out16[M,N] = fp16(act(A16[M,K] @ W16[N,K]^T + bias)); act: 0 none, 1 exact GELU.  K % 8 == 0, N % 8 == 0,
  * block_n: 512 = CTA-pair kernel (256 x 256 tiles, the one the layer GEMMs use), 256 / 128 = single-CTA kernel. */

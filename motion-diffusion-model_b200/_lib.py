@@ -20,7 +20,7 @@ SYMBOLS = [
     "b200mdm_finalize_weights", "b200mdm_set_schedule", "b200mdm_set_cond", "b200mdm_set_cond_dec", "b200mdm_set_prefix",
     "b200mdm_set_inpaint",
     "b200mdm_denoise", "b200mdm_sample_step", "b200mdm_sample_loop", "b200mdm_q_sample", "b200mdm_launch_count",
-    "b200mdm_test_gemm_f16", "b200mdm_test_attention", "b200mdm_test_gemm_resid_ln", "b200mdm_test_layernorm",
+    "b200mdm_recover_from_ric", "b200mdm_test_gemm_f16", "b200mdm_test_attention", "b200mdm_test_gemm_resid_ln", "b200mdm_test_layernorm",
 ]
 
 
@@ -63,6 +63,7 @@ def load():
     lib.b200mdm_set_cond_dec.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, i32, vp]
     lib.b200mdm_set_prefix.argtypes = [vp, vp, vp]
     lib.b200mdm_set_inpaint.argtypes = [vp, vp, vp]
+    lib.b200mdm_recover_from_ric.argtypes = [vp, i64, i64, i64, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp]
     lib.b200mdm_denoise.argtypes = [vp, vp, vp, vp, vp]
     lib.b200mdm_sample_step.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, vp]
     lib.b200mdm_sample_loop.argtypes = [vp, i32, i32, vp, vp, vp, i64, i32, i32, vp]

@@ -22,6 +22,7 @@
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "gemm_ln.cuh"
+#include "postprocess.cuh"
 #include "kernels.cuh"
 
 using namespace b200;
@@ -1179,4 +1180,23 @@ extern "C" int b200mdm_test_layernorm(float* h32_dev, void* h16_dev, const float
                                       int32_t M, void* stream) {
   if (!h32_dev || !h16_dev || !gamma_dev || !beta_dev || M <= 0) return fail(B200MDM_EINVAL, "bad argument");
   return launch_layernorm(h32_dev, static_cast<__half*>(h16_dev), gamma_dev, beta_dev, M, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ post-processing
+extern "C" int b200mdm_recover_from_ric(const float* data_dev, int64_t stride_b, int64_t stride_f, int64_t stride_t,
+                                        const float* mean_dev, const float* std_dev, float* out_dev, int64_t ostride_b,
+                                        int64_t ostride_t, int64_t ostride_c, int32_t batch, int32_t nframes,
+                                        int32_t njoints, void* stream) {
+  if (!data_dev || !out_dev || batch <= 0 || nframes <= 0 || njoints < 2) return fail(B200MDM_EINVAL, "bad argument");
+  if ((mean_dev == nullptr) != (std_dev == nullptr)) return fail(B200MDM_EINVAL, "mean and std come together");
+  const size_t smem = static_cast<size_t>(nframes) * 7 * sizeof(float);
+  if (smem > 48 * 1024) return fail(B200MDM_ENOTIMPL, "recover_from_ric: %d frames exceed the single-CTA scan", nframes);
+  RicArgs a;
+  a.x = data_dev; a.xb = stride_b; a.xf = stride_f; a.xt = stride_t;
+  a.mean = mean_dev; a.std = std_dev;
+  a.out = out_dev; a.ob = ostride_b; a.ot = ostride_t; a.oc = ostride_c;
+  a.T = nframes; a.joints = njoints;
+  recover_from_ric_kernel<<<batch, 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return B200MDM_OK;
 }

@@ -99,3 +99,11 @@ def synthetic_dip_inputs(batch, n_tokens, context_len, njoints=263, nfeats=1, co
         tmask[b, n_tokens - (b * 2) % n_tokens:] = True
     prefix = torch.randn(batch, njoints, nfeats, context_len, generator=g)
     return enc, tmask, prefix
+
+
+def synthetic_norm_stats(dim=263, seed=7):
+    """Stand-in for the dataset's Mean.npy / Std.npy (data_loaders/humanml/data/dataset.py:248-249): fp32 [dim]."""
+    rng = np.random.default_rng(seed)
+    mean = rng.standard_normal(dim).astype(np.float32)
+    std = rng.uniform(0.2, 2.0, size=dim).astype(np.float32)
+    return torch.from_numpy(mean), torch.from_numpy(std)

@@ -15,6 +15,7 @@ Files
                  inpainting loop output, skip_timesteps/init_image output
   enc_c1.npz     BASELINE config 1 shape: L=8, B=1, T=196, 50 steps, CFG 2.5 -> final sample
   a2m_small.npz  action-conditioned trans_enc (humanact12 shape 25x6, 12 classes), no CFG, 3 steps
+  ric.npz        post-loop inv_transform + recover_from_ric (generate.py:161-166), 263- and 251-dim features
   dip_small.npz  trans_dec + BERT-token memory + prefix completion (DiP): L=2, ctx 20 + pred 40, 3 steps, ragged text
                  padding mask, per-sample scales: one CFG forward and the p_sample_loop output
 """
@@ -193,6 +194,24 @@ def gen_dip_small():
     print("dip_small.npz:", {k: v.shape for k, v in out.items() if k != "meta"})
 
 
+def gen_ric():
+    """Post-loop step of sample/generate.py:161-166 (inv_transform + recover_from_ric + permute) by the reference's own
+    functions, HumanML3D (263 -> 22 joints) and KIT (251 -> 21 joints)."""
+    rh.load_reference()
+    mp = importlib.import_module("data_loaders.humanml.scripts.motion_process")
+    out = {"meta": np.array(["sample = randn(torch seed 100+D) [3, D, 1, 40] * 0.8; mean/std = synthetic_norm_stats(D, seed 7)"])}
+    for D, J in ((263, 22), (251, 21)):
+        g = torch.Generator().manual_seed(100 + D)
+        sample = torch.randn(3, D, 1, 40, generator=g) * 0.8
+        mean, std = syn.synthetic_norm_stats(D, seed=7)
+        data = (sample.cpu().permute(0, 2, 3, 1) * std.numpy() + mean.numpy()).float()      # dataset.py:309-310 on numpy stats
+        xyz = mp.recover_from_ric(data, J)
+        out["xyz_%d" % D] = xyz.view(-1, *xyz.shape[2:]).permute(0, 2, 3, 1).contiguous().numpy()
+        out["ric_%d" % D] = mp.recover_from_ric(sample.permute(0, 2, 3, 1).contiguous(), J).numpy()   # no de-normalisation
+    np.savez_compressed(os.path.join(OUT, "ric.npz"), **out)
+    print("ric.npz:", {k: v.shape for k, v in out.items() if k != "meta"})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -202,3 +221,4 @@ if __name__ == "__main__":
     gen_enc_c1()
     gen_a2m_small()
     gen_dip_small()
+    gen_ric()

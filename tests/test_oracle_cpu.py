@@ -115,3 +115,16 @@ def test_oracle_vs_live_reference():
         assert np.array_equal(tabs[k], getattr(diff, k)), k
     o = mo.sample_loop(W, tabs, diff.timestep_map, inp["tape"], inp["text_embed"], inp["scale"], inp["lengths"])
     assert rel_err(o, ref) < TOL
+
+
+def test_recover_from_ric_vs_golden(golden):
+    """Post-loop step (generate.py:161-166): the restatement in oracle/ric_oracle.py against the reference's own
+    inv_transform + recover_from_ric outputs, bit for bit (same torch CPU ops in the same order)."""
+    from oracle import ric_oracle as ro
+    g = golden("ric.npz")
+    for D, J in ((263, 22), (251, 21)):
+        gen = torch.Generator().manual_seed(100 + D)
+        sample = torch.randn(3, D, 1, 40, generator=gen) * 0.8
+        mean, std = b200mdm.synthetic_norm_stats(D, seed=7)
+        assert torch.equal(ro.sample_to_xyz(sample, mean, std), torch.from_numpy(g["xyz_%d" % D]))
+        assert torch.equal(ro.recover_from_ric(sample.permute(0, 2, 3, 1).contiguous(), J), torch.from_numpy(g["ric_%d" % D]))

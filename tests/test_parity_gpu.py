@@ -347,3 +347,41 @@ def test_a2m_config_b256_1000_steps():
     e = rel_err(out[idx], want)
     print("a2m B=256, 1000 steps: relative error vs oracle", e)
     assert e < RTOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Post-loop step: inv_transform + recover_from_ric on the GPU (generate.py:161-166)
+def _ric_close(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def test_recover_from_ric_vs_reference_golden(golden):
+    g = golden("ric.npz")
+    for D, J in ((263, 22), (251, 21)):
+        gen = torch.Generator().manual_seed(100 + D)
+        sample = torch.randn(3, D, 1, 40, generator=gen) * 0.8
+        mean, std = b200mdm.synthetic_norm_stats(D, seed=7)
+        xyz = b200mdm.sample_to_xyz(sample.cuda(), mean.numpy(), std.numpy())
+        assert xyz.shape == (3, J, 3, 40)
+        assert _ric_close(xyz, g["xyz_%d" % D]) < 2e-6           # cosf / sinf are the only non-identical operations
+        ric = b200mdm.recover_from_ric(sample.permute(0, 2, 3, 1).contiguous().cuda(), J)
+        assert ric.shape == (3, 1, 40, J, 3)
+        assert _ric_close(ric, g["ric_%d" % D]) < 2e-6
+    with pytest.raises(RuntimeError):
+        b200mdm.sample_to_xyz(sample, mean, std)                 # CPU tensor: no fallback
+
+
+def test_recover_from_ric_benchmark_size_vs_oracle():
+    """B=64, T=196 (what follows the BASELINE config 2 loop) against the CPU restatement; plus what the construction
+    guarantees exactly: root height is the de-normalised feature 3, frame 0 sits at the origin."""
+    from oracle import ric_oracle as ro
+    gen = torch.Generator().manual_seed(5)
+    sample = torch.randn(64, 263, 1, 196, generator=gen) * 0.5
+    mean, std = b200mdm.synthetic_norm_stats(263, seed=8)
+    xyz = b200mdm.sample_to_xyz(sample.cuda(), mean, std)
+    want = ro.sample_to_xyz(sample, mean, std)
+    assert _ric_close(xyz, want) < 1e-5                          # yaw accumulates over 196 frames
+    h = (sample[:, 3, 0, :] * std[3] + mean[3])
+    assert torch.equal(xyz[:, 0, 1, :].cpu(), h)
+    assert torch.equal(xyz[:, 0, 0, 0].cpu(), torch.zeros(64)) and torch.equal(xyz[:, 0, 2, 0].cpu(), torch.zeros(64))
