@@ -328,8 +328,10 @@ def main():
                 "achieved": round(k_tflops, 1), "peak": peaks["burst"], "unit": "TFLOP/s",
                 "frac": round(k_tflops / peaks["burst"], 4),
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the ncu --set full
-                # capture committed as profiles/r01_b_top_kernel_ncu_metrics.txt (104.4 MB + 22.6 MB)
-                "traffic": 127.06e6, "us": round(k_ms * 1e3, 1),
+                # capture committed as profiles/r01_c_top_kernel_ncu_metrics.txt (104.4 MB read + 16.6 MB written; the
+                # algorithmic bytes are 155.9 MB = A 51.6 + residual in 51.6 + out 51.6 + W 1.0: part of the residual
+                # stream stays in the persisting L2 window)
+                "traffic": 121.0e6, "us": round(k_ms * 1e3, 1),
                 "peak_source": peaks["source"] + " bf16 burst (cuBLAS 8192^3)", "other_kernels": others,
                 "path_achieved_tflops_per_gpu": round(path_tflops, 1),
                 "path_frac_of_sustained": round(path_tflops / peaks["sustained"], 4)}
