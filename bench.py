@@ -54,8 +54,46 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.idx, self.rows, self.proc = gpu_index, [], None
+        self.nvml, self.handle, self.stop_flag, self.thread = None, None, False, None
+
+    # NVML in-process (20 ms period: a 0.4 s timed region still gets ~20 samples); nvidia-smi -lms as the fallback
+    def _nvml_open(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.nvml, self.handle = pynvml, h
+            return True
+        except Exception:
+            return False
+
+    def _nvml_poll(self):
+        n = self.nvml
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+                bits = int(get(self.handle))
+                row = ["", str(sm), str(mx), "", ""] + ["Active" if bits & b else "Not Active" for b in (0x8, 0x40, 0x20, 0x4)]
+                self.rows.append(row)
+            except Exception:
+                pass
+            time.sleep(0.02)
+        del names
 
     def start(self):
+        if self._nvml_open():
+            self.thread = threading.Thread(target=self._nvml_poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
@@ -68,10 +106,14 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+        elif self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
+        else:
+            time.sleep(0.25)
+            self.proc.terminate()
         sm = sorted(int(r[1]) for r in self.rows if len(r) > 2 and r[1].isdigit())
         mx = [int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()]
         reasons = set()
@@ -81,7 +123,8 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows),
+                "source": "nvml 20 ms" if self.thread is not None else "nvidia-smi -lms 200"}
 
 
 def make_args():
