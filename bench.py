@@ -30,6 +30,9 @@ sys.path.insert(0, ROOT)
 B_PER_GPU, T, J, STEPS, L, D, FF, SCALE = 64, 196, 263, 50, 8, 512, 1024, 2.5
 
 
+WORKLOAD = "HumanML3D text2motion B=64/GPU T=196 J=263 50 DDPM steps CFG 2.5 trans_enc L8 d512 ff1024 h4"
+
+
 def flops_per_forward_sample(S=T + 1, d=D, ff=FF, layers=L, jf=J, t=T):
     """F_fwd = L*2S*(3d^2 + d^2 + 2*d*ff + 2*S*d) + 2*(2*T*JF*d)."""
     return layers * 2 * S * (3 * d * d + d * d + 2 * d * ff + 2 * S * d) + 2 * (2 * t * jf * d)
@@ -201,7 +204,8 @@ def run_reference_arm(a, rank, world):
     line = {"impl": "reference", "metric": "motions/sec", "value": round(val, 4), "unit": "motions/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "HumanML3D B=64 T=196 J=263 50 steps CFG 2.5 trans_enc L8 d512 (sample: 4 of 64 motions per step)"},
+            "config": {"workload": WORKLOAD, "global_batch": 64 * max(1, a.gpus),
+                       "sample": "4 of 64 motions per measurement, CPU oracle port of the reference loop"},
             "cpu_baseline": {"value": round(val, 4), "unit": "motions/s", "cores": threads, "kind": "port",
                              "sample": "4 of 64 motions, %d of 50 sampler steps timed per measurement (x2 CFG forwards each), extrapolated to 50; torch fp32; %s" % (nsteps, cpu_model_name())},
             "e2e": {"value": round(val, 4), "unit": "motions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -391,7 +395,7 @@ def main():
                 "warmup": max(a.warmup, 3), "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "fp16 operands / fp32 accumulate (in/out projections hi-lo split)",
                 "data": "synthetic",
-                "config": {"workload": "HumanML3D text2motion B=64/GPU T=196 J=263 50 DDPM steps CFG 2.5 trans_enc L8 d512 ff1024 h4",
+                "config": {"workload": WORKLOAD,
                            "global_batch": B * world, "parallelism": "batch-sharded x%d, 1 NCCL broadcast of text_embed per loop" % world,
                            "l2": "inputs larger than L2 (660 MB noise tape streamed per loop)", "cuda_graph": True},
                 "clocks": clocks, "gpu_launches": int(launches),
