@@ -216,7 +216,8 @@ struct EpiBiasF16Wide {
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// h32[row, col] += acc + bias[col]      (attention out-projection / FFN down-projection + residual, in place).
+// h32[row, col] += acc + bias[col]      (fp32 residual add in place; kept for the GEMM unit tests -- the engine's
+// residual + LayerNorm epilogue lives in gemm_ln.cuh).
 // Per 32-column chunk: TMA load of the residual slab (issued one chunk ahead, three rotating buffers), add in
 // registers, write back into the same slab, TMA store.  map_c: fp32 [M, N], box {32 cols, 32 rows}, SWIZZLE_128B.
 struct EpiResidualF32 {
@@ -285,7 +286,7 @@ struct EpiResidualF32 {
 //   the cond / uncond halves of the packed CFG batch, so every slab is TMA-stored twice (one tensor map per half --
 //   the per-half maps also clip the rows of the last M tile that belong to the other half).  Row s == 0 (the
 //   conditioning token, mdm.py:251) is produced by tok0_rows_kernel right after this GEMM.
-//   Outputs: h32 (fp32 residual stream) and h16 (fp16 copy = next GEMM's A operand).
+//   Output: the residual stream as fp16 [hi | lo] (hi half = the next GEMM's A operand).
 struct EpiEmbed {
   static constexpr int SMEM_PER_WARP = 2 * 4096;  // two [hi | lo] slabs
   static constexpr bool RELEASE_EARLY = true;

@@ -48,7 +48,7 @@ struct GemmLnParams {
   float eps;
 };
 
-// map_a: A [M, K] fp16, box 128 rows; map_b: W [512, K] fp16, box 256 rows; map_h32: h32 [M, 512] fp32, box 32 x 32
+// map_a: A [M, K] fp16, box 128 rows; map_b: W [512, K] fp16, box 256 rows;
 // map_res: the residual stream h, fp16 [M, 1024] = [hi | lo] (hi + lo carries ~22 bits), box {32 cols, 32 rows} with
 // 64-byte rows (SWIZZLE_64B): a 4 KB slab = the hi half-slab of 32 columns + the lo half-slab.  Loaded and stored in place.
 // The hi half doubles as the fp16 A operand of the next GEMM (the trans_dec engine feeds both halves, K = 1024).
