@@ -110,3 +110,58 @@ def test_num_samples_limit_and_no_mm():
     ds = CompMDMGeneratedDataset(args, _Model(), stub, _loader(4), mm_num_samples=0, mm_num_repeats=0, max_motion_length=T,
                                  num_samples_limit=2 * B, scale=1.)
     assert len(ds) == 2 * B and ds.mm_generated_motion == [] and stub.calls == [(B, D, 1, T)] * 2
+
+
+def test_autoregressive_repeats_keep_the_reference_draw_order():
+    """DiP evaluation (args.autoregressive): every repeat is a chain of pred_len chunks, each its own diffusion loop
+    (sampler_util.py:41-81).  Stacked repeats + pre-drawn per-chunk noise must equal the sequential reference structure."""
+    import b200mdm
+    pred, ctx = 5, 2
+    args = SimpleNamespace(autoregressive=True, pred_len=pred, context_len=ctx, autoregressive_include_prefix=False)
+    g = torch.Generator().manual_seed(2)
+
+    def loader():
+        lengths = torch.full((B,), 196)
+        y = dict(lengths=lengths, orig_lengths=lengths.clone(), mask=torch.ones(B, 1, 1, 196, dtype=torch.bool),
+                 text=["c%d" % b for b in range(B)], tokens=["sos/OTHER_eos/OTHER"] * B,
+                 text_embed=torch.randn(1, B, 512, generator=torch.Generator().manual_seed(4)),
+                 prefix=torch.randn(B, D, 1, ctx, generator=torch.Generator().manual_seed(5)))
+
+        class DS(SimpleNamespace):
+            def __len__(self):
+                return 2 * B
+
+        class L(list):
+            batch_size = B
+            dataset = DS(mode="gt", w_vectorizer={"sos/OTHER": (np.zeros(3), np.zeros(2)), "eos/OTHER": (np.zeros(3), np.zeros(2))})
+        return L([(torch.zeros(B, D, 1, 196), {"y": y})])
+
+    class ArStub(_Stub):
+        def p_sample_loop(self, model, shape, noise=None, noise_tape=None, model_kwargs=None, **kw):
+            y = model_kwargs["y"]
+            assert y["prefix"].shape == (shape[0], D, 1, ctx) and shape[-1] == pred
+            out = super().p_sample_loop(model, shape, noise=noise, noise_tape=noise_tape, model_kwargs=model_kwargs)
+            return out + y["prefix"].mean(dim=-1, keepdim=True)          # the chain depends on the handed-over prefix
+
+    np.random.seed(0)
+    torch.manual_seed(21)
+    stub = ArStub()
+    ds = CompMDMGeneratedDataset(args, _Model(), stub, loader(), mm_num_samples=1, mm_num_repeats=2, max_motion_length=196,
+                                 num_samples_limit=None, scale=2.5)
+    n_chunks = 196 // pred + 1
+    assert stub.calls == [(2 * B, D, 1, pred)] * n_chunks                # one stacked loop per chunk
+    # reference structure: for each repeat, AutoRegressiveSampler over sequentially drawn loops
+    torch.manual_seed(21)
+    ref = ArStub()
+    kw = loader()[0][1]
+    y = dict(kw["y"])
+    y["scale"] = torch.ones(B) * 2.5
+    outs = []
+    for t in range(2):
+        sampler = b200mdm.AutoRegressiveSampler(args, ref.p_sample_loop, required_frames=196)
+        outs.append(sampler.sample(None, (B, D, 1, 196), model_kwargs={"y": y}))
+    assert len(ds) == B and len(ds.mm_generated_motion) == B
+    for b in range(B):
+        assert np.array_equal(ds.generated_motion[b]["motion"], outs[0][b].squeeze().permute(1, 0).numpy())
+        for t in range(2):
+            assert np.array_equal(ds.mm_generated_motion[b]["mm_motions"][t]["motion"], outs[t][b].squeeze().permute(1, 0).numpy())
