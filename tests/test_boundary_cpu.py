@@ -112,3 +112,31 @@ def test_no_cpu_fallback():
         model(x, torch.zeros(1, dtype=torch.long), y=y)
     with pytest.raises(RuntimeError):
         diffusion.p_sample_loop(model, (1, 263, 1, 8), clip_denoised=False, model_kwargs={"y": y})
+
+
+def test_c_abi_error_contract_without_gpu():
+    """include/b200mdm.h: every entry point returns 0 or a negative B200MDM_E* code and leaves a message in
+    b200mdm_last_error(); argument validation happens before any CUDA call, so this runs without a GPU."""
+    import ctypes
+    from b200mdm import _lib
+    lib = _lib.load()
+    lib.b200mdm_last_error.restype = ctypes.c_char_p
+    h = ctypes.c_void_p()
+    assert lib.b200mdm_create(None, ctypes.byref(h)) < 0 and b"null" in lib.b200mdm_last_error()
+    cfg = _lib.Config(arch=7, latent_dim=512, ff_size=1024, num_layers=8, num_heads=4, njoints=263, nfeats=1, cond_mode=_lib.COND_TEXT,
+                      cond_dim=512, num_actions=1, mask_frames=1, pos_embed_max_len=5000, temb_rows=1000)
+    assert lib.b200mdm_create(ctypes.byref(cfg), ctypes.byref(h)) < 0 and b"arch 7" in lib.b200mdm_last_error()
+    cfg.arch, cfg.latent_dim = _lib.ARCH["trans_enc"], 256
+    assert lib.b200mdm_create(ctypes.byref(cfg), ctypes.byref(h)) < 0 and b"latent_dim 512" in lib.b200mdm_last_error()
+    cfg.latent_dim, cfg.arch, cfg.cond_mode = 512, _lib.ARCH["trans_dec"], _lib.COND_ACTION
+    assert lib.b200mdm_create(ctypes.byref(cfg), ctypes.byref(h)) < 0 and b"trans_dec" in lib.b200mdm_last_error()
+    assert not h.value
+    # post-processing entry point: pointer / shape checks
+    buf = (ctypes.c_float * 4)()
+    assert lib.b200mdm_recover_from_ric(None, 0, 0, 0, None, None, buf, 0, 0, 0, 1, 1, 22, None) < 0
+    assert lib.b200mdm_recover_from_ric(buf, 1, 1, 1, buf, None, buf, 1, 1, 1, 1, 1, 22, None) < 0 and b"mean and std" in lib.b200mdm_last_error()
+    assert lib.b200mdm_recover_from_ric(buf, 1, 1, 1, None, None, buf, 1, 1, 1, 1, 100000, 22, None) < 0 and b"frames" in lib.b200mdm_last_error()
+    for fn in (lib.b200mdm_set_cond_dec, lib.b200mdm_set_prefix):
+        assert fn.argtypes is not None
+    assert lib.b200mdm_set_prefix(None, None, None) < 0
+    assert lib.b200mdm_version() >= 1
