@@ -12,7 +12,10 @@
  *   - pointers named *_dev are device pointers, *_host host pointers; no ownership is transferred;
  *   - tensors use the reference's layouts: motion x [B, njoints, nfeats, T] fp32 (T contiguous),
  *     text embedding [B, cond_dim] fp32 (the reference's [1, B, C] with the leading 1 dropped);
- *   - nothing allocates on the per-step path: workspaces are (re)built by b200mdm_set_cond for a (B, T) pair;
+ *   - nothing allocates on the per-step path: b200mdm_set_cond selects the workspace of a (B, T, CFG) triple -- built
+ *     on first use, then kept (with its captured step graph) in a small pool;
+ *   - kernels are specialised for latent_dim 512, 4 heads of 128 and sequences of at most 256 tokens (every released
+ *     MDM / DiP model; 196 frames + 1 token); other shapes -> B200MDM_ENOTIMPL;
  *   - no call synchronises the stream except where stated.
  */
 #ifndef B200MDM_H_
@@ -43,6 +46,8 @@ extern "C" {
 
 #define B200MDM_FLAG_CONST_NOISE 1   /* p_sample(const_noise=True): eps row 0 repeated (gaussian_diffusion.py:527-528) */
 #define B200MDM_FLAG_CLIP_DENOISED 2 /* clip_denoised=True: clamp x0 to [-1,1] (gaussian_diffusion.py:348-352) */
+#define B200MDM_FLAG_PHILOX_NOISE 4  /* loops only: eps comes from the engine's counter-based stream (b200mdm_set_noise_stream)
+                                        instead of a caller-provided tape -- replaces th.randn_like, gaussian_diffusion.py:525 */
 
 #define B200MDM_SCHED_STRIDE 8 /* floats per schedule row, see b200mdm_set_schedule */
 
@@ -141,6 +146,25 @@ int b200mdm_sample_loop(b200mdm_engine* e, int32_t mode, int32_t skip_timesteps,
                         const float* noise_tape_dev, int64_t noise_step_stride, int32_t flags, int32_t use_graph,
                         void* stream);
 
+/* The same loop body for a sub-range of the schedule: indices first_index, first_index-1, ... (n_run of them).  This is
+ * what lets the host draw the reference's per-step th.randn_like (gaussian_diffusion.py:525) in bounded chunks instead
+ * of materialising an O(n_steps) tape.  x_in_dev NULL: continue from the state the previous call left in the engine;
+ * x_out_dev NULL: leave the result there.  noise_tape_dev: eps of the k-th step OF THIS CALL at + k*noise_step_stride
+ * (ignored with B200MDM_FLAG_PHILOX_NOISE). */
+int b200mdm_sample_loop_range(b200mdm_engine* e, int32_t mode, int32_t first_index, int32_t n_run, const float* x_in_dev,
+                              float* x_out_dev, const float* noise_tape_dev, int64_t noise_step_stride, int32_t flags,
+                              int32_t use_graph, void* stream);
+
+/* The engine's own noise stream (no reference counterpart: the reference draws from torch's global generator).
+ * Philox4x32-10 keyed by `seed`, counter = (element/4, schedule index of the consuming step, global sample index);
+ * Box-Muller on the 4 output words (exact recipe: csrc/kernels.cuh, restated in oracle/philox_oracle.py).  A sample's
+ * noise depends only on (seed, its global index, step, element): sharding the batch over GPUs, or drawing the steps in
+ * chunks, cannot change it.  sample_index_base = global index of this engine's sample 0. */
+int b200mdm_set_noise_stream(b200mdm_engine* e, uint64_t seed, int64_t sample_index_base);
+/* out[b, :] = that stream for step_id (x_T uses step_id = -1), b = 0..batch-1, n_per_sample fp32 each. */
+int b200mdm_philox_normal(float* out_dev, int32_t batch, int64_t n_per_sample, uint64_t seed, int64_t sample_index_base,
+                          int32_t step_id, void* stream);
+
 /* q_sample (gaussian_diffusion.py:226-244) at schedule index `index`: out = sqrt_ac*x_start + sqrt_1mac*noise;
  * x_start_dev NULL => zeros (gaussian_diffusion.py:693-694).  sqrt_ac / sqrt_1mac are the fp32 table values. */
 int b200mdm_q_sample(b200mdm_engine* e, float sqrt_ac, float sqrt_1mac, const float* x_start_dev,
@@ -162,21 +186,25 @@ int b200mdm_recover_from_ric(const float* data_dev, int64_t stride_b, int64_t st
 
 /* ---- kernel-level entry points (used by tests/ to check each kernel against a torch fp32 restatement) ---- */
 /* out16[M,N] = fp16(act(A16[M,K] @ W16[N,K]^T + bias)); act: 0 none, 1 exact GELU.  K % 8 == 0, N % 8 == 0,
- * block_n: 512 = CTA-pair kernel (256 x 256 tiles, the one the layer GEMMs use), 256 / 128 = single-CTA kernel. */
+ * block_n: 512 = CTA-pair kernel (256 x 256 tiles, the one the layer GEMMs use), 128 = single-CTA kernel (the mainloop
+ * the embedding / output projections use). */
 int b200mdm_test_gemm_f16(const void* a16_dev, const void* w16_dev, const float* bias_dev, void* out16_dev, int32_t M,
                           int32_t N, int32_t K, int32_t act, int32_t block_n, void* stream);
 /* out16[n*S, d] = softmax(q k^T / sqrt(128) + mask) v per (sample, head); qkv16 [n*S, 3d]; kvlen int32 [n] device.
- * impl 0: tcgen05 kernel (S <= 256, the one the engine uses); impl 1: mma.sync kernel for longer sequences. */
+ * impl must be 0 (tcgen05 kernel, S <= 256). */
 int b200mdm_test_attention(const void* qkv16_dev, void* out16_dev, const int32_t* kvlen_dev, int32_t n_samples,
                            int32_t S, int32_t d, int32_t impl, void* stream);
+/* The fused QKV-projection + attention kernel of the encoder layers (nn.MultiheadAttention up to its output projection,
+ * model/mdm.py:77-84): out16[n*S, 512] = concat_h softmax((h Wq_h^T + bq)(h Wk_h^T + bk)^T / sqrt(128) + mask)(h Wv_h^T + bv).
+ * h16: fp16 [n*S, ld] (first 512 columns used), wqkv16: in_proj_weight fp16 [1536, 512], bqkv fp32 [1536],
+ * kvlen int32 [n] device (valid keys per sample), S <= 256. */
+int b200mdm_test_qkv_attention(const void* h16_dev, int32_t ld, const void* wqkv16_dev, const float* bqkv_dev,
+                               void* out16_dev, const int32_t* kvlen_dev, int32_t n_samples, int32_t S, void* stream);
 /* h[M,512] <- LayerNorm(h + A16[M,K] @ W16[512,K]^T + bias; gamma, beta, 1e-5) in place (the fused out-projection /
  * FFN-down kernel of the transformer layer).  h is the engine's residual-stream format: fp16 [M, 1024] = [hi | lo],
  * value = hi + lo.  K % 8 == 0. */
 int b200mdm_test_gemm_resid_ln(const void* a16_dev, const void* w16_dev, const float* bias_dev, const float* gamma_dev,
                                const float* beta_dev, void* hres16_dev, int32_t M, int32_t K, void* stream);
-/* in-place LayerNorm over rows of h32 [M,512] + fp16 copy */
-int b200mdm_test_layernorm(float* h32_dev, void* h16_dev, const float* gamma_dev, const float* beta_dev, int32_t M,
-                           void* stream);
 
 #ifdef __cplusplus
 }

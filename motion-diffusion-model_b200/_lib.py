@@ -12,6 +12,7 @@ OK, EINVAL, ECUDA, ESTATE, ENOTIMPL = 0, -1, -2, -3, -4
 ARCH = {"trans_enc": 0, "trans_dec": 1}
 COND_NONE, COND_TEXT, COND_ACTION = 0, 1, 2
 MODE_X0, MODE_DDPM, MODE_DDIM = 0, 1, 2
+FLAG_CONST_NOISE, FLAG_CLIP_DENOISED, FLAG_PHILOX_NOISE = 1, 2, 4
 SCHED_STRIDE = 8
 
 # every symbol include/b200mdm.h declares (tests check that the library exports all of them)
@@ -20,7 +21,8 @@ SYMBOLS = [
     "b200mdm_finalize_weights", "b200mdm_set_schedule", "b200mdm_set_cond", "b200mdm_set_cond_dec", "b200mdm_set_prefix",
     "b200mdm_set_inpaint",
     "b200mdm_denoise", "b200mdm_sample_step", "b200mdm_sample_loop", "b200mdm_q_sample", "b200mdm_launch_count",
-    "b200mdm_recover_from_ric", "b200mdm_test_gemm_f16", "b200mdm_test_attention", "b200mdm_test_gemm_resid_ln", "b200mdm_test_layernorm",
+    "b200mdm_sample_loop_range", "b200mdm_set_noise_stream", "b200mdm_philox_normal",
+    "b200mdm_recover_from_ric", "b200mdm_test_gemm_f16", "b200mdm_test_attention", "b200mdm_test_qkv_attention", "b200mdm_test_gemm_resid_ln",
 ]
 
 
@@ -67,13 +69,16 @@ def load():
     lib.b200mdm_denoise.argtypes = [vp, vp, vp, vp, vp]
     lib.b200mdm_sample_step.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, vp]
     lib.b200mdm_sample_loop.argtypes = [vp, i32, i32, vp, vp, vp, i64, i32, i32, vp]
+    lib.b200mdm_sample_loop_range.argtypes = [vp, i32, i32, i32, vp, vp, vp, i64, i32, i32, vp]
+    lib.b200mdm_set_noise_stream.argtypes = [vp, ctypes.c_uint64, i64]
+    lib.b200mdm_philox_normal.argtypes = [vp, i32, i64, ctypes.c_uint64, i64, i32, vp]
     lib.b200mdm_q_sample.argtypes = [vp, f32, f32, vp, vp, vp, i64, vp]
     lib.b200mdm_launch_count.argtypes = [vp, i32]
     lib.b200mdm_launch_count.restype = i64
     lib.b200mdm_test_gemm_f16.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.b200mdm_test_attention.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.b200mdm_test_qkv_attention.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, vp]
     lib.b200mdm_test_gemm_resid_ln.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
-    lib.b200mdm_test_layernorm.argtypes = [vp, vp, vp, vp, i32, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is ctypes.c_int and name not in ("b200mdm_version",):

@@ -16,13 +16,13 @@
 #include <vector>
 
 #include "../../include/b200mdm.h"
-#include "attention.cuh"
 #include "attention_tc.cuh"
 #include "epilogues.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "gemm_ln.cuh"
 #include "postprocess.cuh"
+#include "qkv_attn.cuh"
 #include "kernels.cuh"
 
 using namespace b200;
@@ -126,6 +126,7 @@ struct LayerW {
   __half *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
   const float *bqkv, *bo, *b1, *b2, *g1, *be1, *g2, *be2;
   CUtensorMap m_wqkv, m_wo, m_w1, m_w2;   // box 128 rows: each CTA of a pair stages half of a 256-row W tile
+  CUtensorMap m_wqkv_64;                  // box 64 rows: the V half-tiles of the fused QKV + attention kernel
   CUtensorMap m_wo_256, m_w2_256;         // box 256 rows: residual+LayerNorm kernel (each CTA owns 256 output columns)
   // trans_dec only: cross-attention (multihead_attn) projections and the third LayerNorm
   __half *wq_c = nullptr, *wkv_c = nullptr, *wo_c = nullptr;
@@ -142,7 +143,38 @@ struct GraphKey {
   }
 };
 
-struct b200mdm_engine {
+// Everything sized by (batch, nframes, CFG halves): activations, their TMA maps, the conditioning rows and the captured
+// step graph (whose kernel parameters are these very pointers).  The engine keeps the workspace in use as its own
+// base-class fields and parks the others in a small pool, so callers that alternate between shapes (the evaluation
+// loader: 32 <-> 32 x mm_num_repeats, comp_v6_model_dataset.py:148-256) neither re-allocate nor re-capture.
+struct Workspace {
+  int B = 0, T = 0, S = 0, halves = 1, Bp = 0, M = 0, MB = 0;
+  __half *xin16 = nullptr, *hres = nullptr, *qkv16 = nullptr, *att16 = nullptr, *ffn16 = nullptr, *g16 = nullptr;
+  float *tok0 = nullptr, *condproj = nullptr, *proj = nullptr, *scale = nullptr, *x_work = nullptr, *eps_buf = nullptr;
+  int *kvlen = nullptr, *tvec = nullptr, *action = nullptr;
+  CUtensorMap m_xin, m_h16, m_att, m_ffn, m_g16;      // A operands (loads, box 128 rows)
+  CUtensorMap m_qkv_st, m_ffn_st;                      // epilogue slabs (box 32 rows x 128 bytes)
+  CUtensorMap m_res;                                   // residual stream [hi | lo] (make_map_res)
+  CUtensorMap m_att_q, m_att_kv, m_att_o;             // tcgen05 attention: per-sample 3-D views of qkv16 / att16
+  CUtensorMap m_h3;                                    // fused QKV+attention: per-sample A tiles of the stream's hi half
+  CUtensorMap m_res_c, m_res_u;                        // per-CFG-half views of the residual stream (embedding epilogue)
+  float* pe_bias = nullptr;
+  bool cond_set = false;
+  // trans_dec (DiP): prefix frames + text-token memory
+  int Mt = 0;
+  float *encperm = nullptr, *memtok = nullptr, *memproj = nullptr;   // [B*Mt, cond_dim], [B*Mt, d], [Bp*Mt, d]
+  __half *mem16 = nullptr, *qc16 = nullptr, *kvc16 = nullptr;        // [Bp*Mt, d], [M, d], [Bp*Mt, 2d]
+  unsigned char* memmask = nullptr;                                   // [Bp, Mt] 1 = padding
+  CUtensorMap m_mem, m_qc_st, m_kvc_st;
+  bool prefix_set = false;
+  // captured step graph of this workspace
+  cudaGraphExec_t graph_exec = nullptr;
+  GraphKey graph_key;
+  int graph_kernels = 0;
+  unsigned long long last_use = 0;
+};
+
+struct b200mdm_engine : Workspace {
   b200mdm_config cfg;
   int d, ff, L, H, JF, Kp_in, N_out_pad;
   int num_sms = 148;
@@ -154,40 +186,29 @@ struct b200mdm_engine {
   std::vector<LayerW> layers;
   const float *b_in = nullptr, *b_out = nullptr, *pe = nullptr, *w_txt = nullptr, *b_txt = nullptr, *act_emb = nullptr;
   float *temb_hidden = nullptr, *temb_table = nullptr;
-  // schedule
+  // schedule (device tables are allocated once at `sched_cap` rows: the step graphs hold these pointers)
   float* sched = nullptr;
   int* tmap = nullptr;
-  int n_steps = 0;
-  // per-(B,T) workspace
-  int B = 0, T = 0, S = 0, halves = 1, Bp = 0, M = 0, MB = 0;
-  __half *xin16 = nullptr, *hres = nullptr, *qkv16 = nullptr, *att16 = nullptr, *ffn16 = nullptr, *g16 = nullptr;
-  float *tok0 = nullptr, *condproj = nullptr, *proj = nullptr, *scale = nullptr, *x_work = nullptr;
-  int *kvlen = nullptr, *tvec = nullptr, *action = nullptr;
-  StepState* state = nullptr;
-  CUtensorMap m_xin, m_h16, m_att, m_ffn, m_g16;      // A operands (loads, box 128 rows)
-  CUtensorMap m_qkv_st, m_ffn_st;                      // epilogue slabs (box 32 rows x 128 bytes)
-  CUtensorMap m_res;                                   // residual stream [hi | lo] (make_map_res)
-  CUtensorMap m_att_q, m_att_kv, m_att_o;             // tcgen05 attention: per-sample 3-D views of qkv16 / att16
-  CUtensorMap m_res_c, m_res_u;                        // per-CFG-half views of the residual stream (embedding epilogue)
-  float* pe_bias = nullptr;
-  bool cond_set = false;
-  // trans_dec (DiP): prefix frames + text-token memory
+  int n_steps = 0, sched_cap = 0;
+  // parked workspaces (see Workspace)
+  std::vector<Workspace> pool;
+  unsigned long long use_clock = 0;
+  // host staging for b200mdm_set_cond* (kept alive until the next call: no stream synchronisation needed)
+  std::vector<int> h_kv, h_action;
+  std::vector<unsigned char> h_mask;
+  // trans_dec (DiP)
   bool dec = false;
-  int ctx = 0, s_off = 1, Mt = 0;
+  int ctx = 0, s_off = 1;
   int kw = 1;   // 2: fp16 activations between the layer GEMMs are [hi | lo] pairs along K (trans_dec engine)
-  float *encperm = nullptr, *memtok = nullptr, *memproj = nullptr;   // [B*Mt, cond_dim], [B*Mt, d], [Bp*Mt, d]
-  __half *mem16 = nullptr, *qc16 = nullptr, *kvc16 = nullptr;        // [Bp*Mt, d], [M, d], [Bp*Mt, 2d]
-  unsigned char* memmask = nullptr;                                   // [Bp, Mt] 1 = padding
-  CUtensorMap m_mem, m_qc_st, m_kvc_st;
-  bool prefix_set = false;
   const unsigned char* inpaint_mask = nullptr;
   const float* inpaint_motion = nullptr;
+  // in-engine noise (B200MDM_FLAG_PHILOX_NOISE): counter-based Philox4x32-10 keyed by (seed, schedule index, global sample)
+  unsigned long long noise_seed = 0;
+  long long noise_sample_base = 0;
   // loop machinery
+  StepState* state = nullptr;   // device-side step counter + per-loop noise description, shared by every workspace
   cudaStream_t work = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-  cudaGraphExec_t graph_exec = nullptr;
-  GraphKey graph_key;
-  int graph_kernels = 0;
   long long launches = 0;
 };
 
@@ -216,26 +237,25 @@ static int set_gemm2_attr() {
   return B200MDM_OK;
 }
 static int init_kernel_attrs() {
-  static bool done = false;
-  if (done) return B200MDM_OK;
-  TRY((set_gemm_attr<256, EpiBiasF16<false>>()));
-  TRY((set_gemm_attr<256, EpiBiasF16<true>>()));
+  // function attributes are per device: track which ordinals have been initialised
+  static unsigned long long done_mask = 0;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 64 && ((done_mask >> dev) & 1ull)) return B200MDM_OK;
   TRY((set_gemm_attr<128, EpiBiasF16<false>>()));
   TRY((set_gemm_attr<128, EpiBiasF16<true>>()));
-  TRY((set_gemm_attr<256, EpiResidualF32>()));
   TRY((set_gemm2_attr<EpiBiasF16<false>>()));
   TRY((set_gemm2_attr<EpiBiasF16<true>>()));
-  TRY((set_gemm2_attr<EpiResidualF32>()));
   TRY((set_gemm2_attr<EpiBiasF16Wide<true>>()));
   CUDA_TRY(cudaFuncSetAttribute(gemm_resid_ln_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLnSmem::TOTAL));
   TRY((set_gemm_attr<128, EpiEmbed>()));
   TRY((set_gemm_attr<96, EpiOutStep>()));
-  CUDA_TRY(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(qkv_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QkvAttnSmem::TOTAL));
   CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 AttnTcSmem::total(ATC_MAX_KEYS)));
   CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 AttnTcSmem::total(ATC_MAX_KEYS)));
-  done = true;
+  if (dev < 64) done_mask |= 1ull << dev;
   return B200MDM_OK;
 }
 
@@ -307,18 +327,6 @@ static int launch_gemm_resid_ln(const CUtensorMap& a, const CUtensorMap& w256, c
   return B200MDM_OK;
 }
 
-static int launch_attention_mma(const __half* qkv, __half* out, const int* kvlen, int n_samples, int S, int d, int H,
-                                cudaStream_t s) {
-  const int S_pad = (S + 15) & ~15;
-  const size_t smem = static_cast<size_t>(S_pad) * 512;
-  if (smem > 220 * 1024) return fail(B200MDM_ENOTIMPL, "attention: sequence of %d tokens exceeds the resident-KV kernel", S);
-  if (d != H * ATT_DH) return fail(B200MDM_ENOTIMPL, "attention: head_dim must be 128");
-  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(ATT_DH));
-  attention_mma_kernel<<<dim3(H, n_samples), ATT_THREADS, smem, s>>>(qkv, out, kvlen, S, d, scale_log2);
-  CUDA_TRY(cudaGetLastError());
-  return B200MDM_OK;
-}
-
 struct AttnMaps {
   CUtensorMap q, kv, o;
 };
@@ -341,10 +349,25 @@ static int launch_attention_tc(const AttnMaps& m, const int* kvlen, int n_sample
   return B200MDM_OK;
 }
 
-static int launch_layernorm(float* h32, __half* h16, const float* g, const float* b, int M, cudaStream_t s) {
-  layernorm512_kernel<<<(M + 7) / 8, 256, 0, s>>>(h32, h16, g, b, M, 1e-5f);
-  CUDA_TRY(cudaGetLastError());
+// fused QKV projection + attention (qkv_attn.cuh): one CTA pair per (sample, head), persistent
+static int launch_qkv_attention(const CUtensorMap& h3, const CUtensorMap& w128, const CUtensorMap& w64, const CUtensorMap& o,
+                                const float* bqkv, const int* kvlen, int n_samples, int S, cudaStream_t s, int num_sms) {
+  if (S > 256) return fail(B200MDM_ENOTIMPL, "fused attention: at most 256 tokens per sample");
+  const int items = n_samples * 4;
+  const int max_clusters = num_sms / 2;
+  const int clusters = items < max_clusters ? items : max_clusters;
+  const float scale_log2 = 1.4426950408889634f / sqrtf(128.0f);
+  CUDA_TRY(launch_k(qkv_attention_kernel, dim3(2 * clusters), dim3(QA_THREADS), QkvAttnSmem::TOTAL, s, h3, w128, w64, o, bqkv, kvlen,
+                    n_samples, S, scale_log2));
   return B200MDM_OK;
+}
+static bool fused_qkv_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200MDM_FUSED_QKV");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 // ------------------------------------------------------------------------------------------------ API: basics
@@ -395,26 +418,35 @@ extern "C" int b200mdm_create(const b200mdm_config* cfg, b200mdm_engine** out) {
   return B200MDM_OK;
 }
 
-static void free_workspace(b200mdm_engine* e) {
-  dfree(e->xin16); dfree(e->hres); dfree(e->qkv16); dfree(e->att16); dfree(e->ffn16); dfree(e->g16);
-  dfree(e->tok0); dfree(e->condproj); dfree(e->proj); dfree(e->scale); dfree(e->x_work); dfree(e->pe_bias);
-  dfree(e->kvlen); dfree(e->tvec); dfree(e->action);
-  dfree(e->encperm); dfree(e->memtok); dfree(e->memproj); dfree(e->mem16); dfree(e->qc16); dfree(e->kvc16); dfree(e->memmask);
-  e->Mt = 0; e->prefix_set = false;
-  e->B = e->T = 0;
-  e->cond_set = false;
+static void drop_graph(Workspace* w) {
+  if (w->graph_exec) cudaGraphExecDestroy(w->graph_exec);
+  w->graph_exec = nullptr;
+  w->graph_key = GraphKey();
 }
-static void drop_graph(b200mdm_engine* e) {
-  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
-  e->graph_exec = nullptr;
-  e->graph_key = GraphKey();
+static void free_workspace(Workspace* w) {
+  drop_graph(w);
+  dfree(w->xin16); dfree(w->hres); dfree(w->qkv16); dfree(w->att16); dfree(w->ffn16); dfree(w->g16);
+  dfree(w->tok0); dfree(w->condproj); dfree(w->proj); dfree(w->scale); dfree(w->x_work); dfree(w->pe_bias); dfree(w->eps_buf);
+  dfree(w->kvlen); dfree(w->tvec); dfree(w->action);
+  dfree(w->encperm); dfree(w->memtok); dfree(w->memproj); dfree(w->mem16); dfree(w->qc16); dfree(w->kvc16); dfree(w->memmask);
+  *w = Workspace();
+}
+// every workspace (the one in use and the parked ones): after a weight reload or a schedule-table move their graphs
+// and derived tables (pe_bias, condproj, memproj) are stale
+static void free_all_workspaces(b200mdm_engine* e) {
+  free_workspace(static_cast<Workspace*>(e));
+  for (auto& w : e->pool) free_workspace(&w);
+  e->pool.clear();
+}
+static void drop_all_graphs(b200mdm_engine* e) {
+  drop_graph(static_cast<Workspace*>(e));
+  for (auto& w : e->pool) drop_graph(&w);
 }
 
 extern "C" int b200mdm_destroy(b200mdm_engine* e) {
   if (!e) return B200MDM_OK;
   cudaDeviceSynchronize();
-  drop_graph(e);
-  free_workspace(e);
+  free_all_workspaces(e);
   for (auto& kv : e->store) cudaFree(kv.second.dev);
   for (auto& l : e->layers) { dfree(l.wqkv); dfree(l.wo); dfree(l.w1); dfree(l.w2); dfree(l.wq_c); dfree(l.wkv_c); dfree(l.wo_c); }
   dfree(e->w_in3); dfree(e->w_out3); dfree(e->temb_hidden); dfree(e->temb_table); dfree(e->sched); dfree(e->tmap);
@@ -524,8 +556,11 @@ extern "C" int b200mdm_finalize_weights(b200mdm_engine* e, void* stream) {
   }
   if (e->cfg.temb_rows > e->cfg.pos_embed_max_len) return fail(B200MDM_EINVAL, "temb_rows exceeds the positional table");
 
-  // drop previous repacks
-  drop_graph(e);
+  // drop previous repacks; every workspace holds tables derived from the weights (pe_bias, condproj, memproj) and a
+  // graph whose kernel parameters point at the old repacks: a forward that ran before this load must not leak into
+  // the next one
+  CUDA_TRY(cudaDeviceSynchronize());
+  free_all_workspaces(e);
   for (auto& l : e->layers) { dfree(l.wqkv); dfree(l.wo); dfree(l.w1); dfree(l.w2); dfree(l.wq_c); dfree(l.wkv_c); dfree(l.wo_c); }
   dfree(e->w_in3); dfree(e->w_out3); dfree(e->temb_hidden); dfree(e->temb_table);
 
@@ -562,6 +597,7 @@ extern "C" int b200mdm_finalize_weights(b200mdm_engine* e, void* stream) {
     TRY(to_f16_k(w1, &w.w1, ff, d, kw, s));
     TRY(to_f16_k(w2, &w.w2, d, ff, kw, s));
     TRY(make_map(&w.m_wqkv, w.wqkv, 3 * d, kw * d, kw * d, 128));
+    TRY(make_map(&w.m_wqkv_64, w.wqkv, 3 * d, kw * d, kw * d, 64));
     TRY(make_map(&w.m_wo, w.wo, d, kw * d, kw * d, 128));
     TRY(make_map(&w.m_w1, w.w1, ff, kw * d, kw * d, 128));
     TRY(make_map(&w.m_w2, w.w2, d, kw * ff, kw * ff, 128));
@@ -609,23 +645,27 @@ extern "C" int b200mdm_set_schedule(b200mdm_engine* e, int32_t n_steps, const fl
     if (timestep_map_host[i] < 0 || timestep_map_host[i] >= e->cfg.temb_rows)
       return fail(B200MDM_EINVAL, "timestep_map[%d] = %d outside the pre-embedded range [0, %d)", i, timestep_map_host[i],
                   e->cfg.temb_rows);
-  if (n_steps != e->n_steps) {
+  CUDA_TRY(cudaDeviceSynchronize());  // a loop still in flight may be reading the old tables
+  if (n_steps > e->sched_cap) {
+    // the captured step graphs hold these pointers as kernel parameters: moving the tables invalidates every graph
+    drop_all_graphs(e);
     dfree(e->sched);
     dfree(e->tmap);
-    TRY(dalloc(&e->sched, static_cast<size_t>(n_steps) * SCHED_STRIDE));
-    TRY(dalloc(&e->tmap, n_steps));
-    e->n_steps = n_steps;
+    const int cap = n_steps > 1000 ? n_steps : 1000;
+    TRY(dalloc(&e->sched, static_cast<size_t>(cap) * SCHED_STRIDE));
+    TRY(dalloc(&e->tmap, cap));
+    e->sched_cap = cap;
   }
-  CUDA_TRY(cudaDeviceSynchronize());  // a loop still in flight may be reading the old tables
+  e->n_steps = n_steps;
   CUDA_TRY(cudaMemcpy(e->sched, rows_host, static_cast<size_t>(n_steps) * SCHED_STRIDE * sizeof(float), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(e->tmap, timestep_map_host, static_cast<size_t>(n_steps) * sizeof(int), cudaMemcpyHostToDevice));
   return B200MDM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ cond / workspace
-static int build_workspace(b200mdm_engine* e, int B, int T, int halves) {
-  drop_graph(e);
-  free_workspace(e);
+static void attach_l2_window(b200mdm_engine* e);
+
+static int build_workspace(b200mdm_engine* e, int B, int T, int halves, cudaStream_t s) {
   const int d = e->d, S = T + e->s_off, Bp = halves * B;
   const size_t M = static_cast<size_t>(Bp) * S, MB = static_cast<size_t>(B) * S;
   TRY(dalloc(&e->xin16, MB * 3 * e->Kp_in, true));
@@ -651,27 +691,7 @@ static int build_workspace(b200mdm_engine* e, int B, int T, int halves) {
   }
   e->B = B; e->T = T; e->S = S; e->halves = halves; e->Bp = Bp;
   e->M = static_cast<int>(M); e->MB = static_cast<int>(MB);
-  // Keep the fp32 residual stream resident in the L2 (126 MB): it is read and rewritten by every residual+LayerNorm
-  // GEMM, and between two of them ~230 MB of other activations stream through.  The window is attached to the engine
-  // stream, so every kernel captured into the step graph inherits it.  Best effort: failures are ignored.
-  {
-    cudaDeviceProp prop;
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
-      const size_t want = M * d * 2 * sizeof(__half);
-      const size_t carve = want < static_cast<size_t>(prop.persistingL2CacheMaxSize) ? want : static_cast<size_t>(prop.persistingL2CacheMaxSize);
-      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
-      cudaStreamAttrValue attr;
-      memset(&attr, 0, sizeof(attr));
-      attr.accessPolicyWindow.base_ptr = e->hres;
-      attr.accessPolicyWindow.num_bytes = want < static_cast<size_t>(prop.accessPolicyMaxWindowSize) ? want : static_cast<size_t>(prop.accessPolicyMaxWindowSize);
-      attr.accessPolicyWindow.hitRatio = want <= carve ? 1.0f : static_cast<float>(carve) / static_cast<float>(want);
-      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      cudaStreamSetAttribute(e->work, cudaStreamAttributeAccessPolicyWindow, &attr);
-      cudaGetLastError();
-    }
-  }
+  attach_l2_window(e);
   TRY(make_map(&e->m_xin, e->xin16, MB, 3 * e->Kp_in, 3 * e->Kp_in, GEMM_BLOCK_M));
   // GEMM A operand = the hi half of the residual stream (kw = 2, trans_dec: both halves, K = 2d against [W | W])
   TRY(make_map(&e->m_h16, e->hres, M, kw * d, 2 * d, GEMM_BLOCK_M));
@@ -681,7 +701,7 @@ static int build_workspace(b200mdm_engine* e, int B, int T, int halves) {
   TRY(make_map_t(&e->m_qkv_st, e->qkv16, 2, M, 3 * d, 3 * d, 32));
   TRY(make_map_t(&e->m_ffn_st, e->ffn16, 2, M, kw * e->ff, kw * e->ff, 32));
   TRY(make_map_res(&e->m_res, e->hres, M, d));
-  if (S <= ATC_MAX_KEYS) {
+  {
     AttnMaps am;
     TRY(make_attn_maps(&am, e->qkv16, e->att16, Bp, S, d, kw));
     e->m_att_q = am.q; e->m_att_kv = am.kv; e->m_att_o = am.o;
@@ -689,11 +709,73 @@ static int build_workspace(b200mdm_engine* e, int B, int T, int halves) {
   TRY(make_map_res(&e->m_res_c, e->hres, MB, d));
   TRY(make_map_res(&e->m_res_u, e->hres + (halves == 2 ? MB * d * 2 : 0), MB, d));
   TRY(dalloc(&e->pe_bias, static_cast<size_t>(S) * d));
-  pe_bias_kernel<<<S, 128>>>(e->pe_bias, e->pe, e->b_in, S, d);
+  pe_bias_kernel<<<S, 128, 0, s>>>(e->pe_bias, e->pe, e->b_in, S, d);   // on the caller's stream: ordered before any forward
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaDeviceSynchronize());
+  TRY(dalloc(&e->eps_buf, static_cast<size_t>(B) * e->JF * T));
+  // fused QKV + attention (qkv_attn.cuh): per-sample 3-D view of the stream's hi half (A tiles of 128 tokens that stop
+  // at the sample's last token) and of att16 (128-row output tiles clipped the same way)
+  TRY(make_map_3d(&e->m_h3, e->hres, Bp, S, d, 2 * d, 128));
   return B200MDM_OK;
 }
+
+// Keep the residual stream resident in the L2 (126 MB): it is read and rewritten by every residual+LayerNorm GEMM, and
+// between two of them ~230 MB of other activations stream through.  The window is attached to the engine stream, so
+// every kernel captured into the step graph inherits it.  Best effort: failures are ignored.
+static void attach_l2_window(b200mdm_engine* e) {
+  cudaDeviceProp prop;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+    const size_t want = static_cast<size_t>(e->M) * e->d * 2 * sizeof(__half);
+    const size_t carve = want < static_cast<size_t>(prop.persistingL2CacheMaxSize) ? want : static_cast<size_t>(prop.persistingL2CacheMaxSize);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = e->hres;
+    attr.accessPolicyWindow.num_bytes = want < static_cast<size_t>(prop.accessPolicyMaxWindowSize) ? want : static_cast<size_t>(prop.accessPolicyMaxWindowSize);
+    attr.accessPolicyWindow.hitRatio = want <= carve ? 1.0f : static_cast<float>(carve) / static_cast<float>(want);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(e->work, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();
+  }
+}
+
+// Make the workspace for (B, T, halves) the current one: the one in use if it matches, else a parked one, else a new
+// one (the least recently used of more than `MAX_PARKED` parked workspaces is freed).
+static int select_workspace(b200mdm_engine* e, int B, int T, int halves, cudaStream_t s) {
+  constexpr size_t MAX_PARKED = 3;
+  Workspace* cur = static_cast<Workspace*>(e);
+  e->last_use = ++e->use_clock;
+  if (cur->B == B && cur->T == T && cur->halves == halves) return B200MDM_OK;
+  if (cur->B > 0) {
+    e->pool.push_back(*cur);
+    *cur = Workspace();
+  }
+  for (size_t i = 0; i < e->pool.size(); ++i) {
+    if (e->pool[i].B == B && e->pool[i].T == T && e->pool[i].halves == halves) {
+      *cur = e->pool[i];
+      e->pool.erase(e->pool.begin() + i);
+      cur->last_use = e->use_clock;
+      cur->cond_set = false;      // the caller is about to set the conditioning of this loop
+      cur->prefix_set = false;
+      attach_l2_window(e);
+      return B200MDM_OK;
+    }
+  }
+  while (e->pool.size() > MAX_PARKED) {
+    size_t lru = 0;
+    for (size_t i = 1; i < e->pool.size(); ++i)
+      if (e->pool[i].last_use < e->pool[lru].last_use) lru = i;
+    CUDA_TRY(cudaDeviceSynchronize());   // a loop on that workspace may still be running
+    free_workspace(&e->pool[lru]);
+    e->pool.erase(e->pool.begin() + lru);
+  }
+  int r = build_workspace(e, B, T, halves, s);
+  if (r != B200MDM_OK) free_workspace(cur);
+  cur->last_use = e->use_clock;
+  return r;
+}
+
 
 extern "C" int b200mdm_set_cond(b200mdm_engine* e, int32_t batch, int32_t nframes, const float* cond_embed_dev,
                                 const int64_t* lengths_host, const float* scale_dev, int32_t force_uncond,
@@ -703,6 +785,9 @@ extern "C" int b200mdm_set_cond(b200mdm_engine* e, int32_t batch, int32_t nframe
   if (!e->finalized) return fail(B200MDM_ESTATE, "weights not finalised");
   if (batch <= 0 || nframes <= 0) return fail(B200MDM_EINVAL, "bad batch / nframes");
   if (nframes + 1 > e->cfg.pos_embed_max_len) return fail(B200MDM_EINVAL, "sequence longer than the positional table");
+  if (nframes + 1 > ATC_MAX_KEYS)
+    return fail(B200MDM_ENOTIMPL, "sequences of more than %d tokens (the attention kernels keep all keys of a sample on chip; "
+                "every dataset of the reference stops at 196 frames)", ATC_MAX_KEYS);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int halves = scale_dev ? 2 : 1;
   if (e->cfg.cond_mode == B200MDM_COND_TEXT && !cond_embed_dev && !(halves == 1 && force_uncond))
@@ -711,13 +796,12 @@ extern "C" int b200mdm_set_cond(b200mdm_engine* e, int32_t batch, int32_t nframe
     return fail(B200MDM_EINVAL, "action-conditioned model needs y['action']");
   if (halves == 2 && e->cfg.cond_mode == B200MDM_COND_NONE)
     return fail(B200MDM_EINVAL, "classifier-free guidance needs a conditioned model (sampler_util.py:29)");
-  if (batch != e->B || nframes != e->T || halves != e->halves) {
-    CUDA_TRY(cudaDeviceSynchronize());
-    TRY(build_workspace(e, batch, nframes, halves));
-  }
+  TRY(select_workspace(e, batch, nframes, halves, s));
   const int d = e->d, B = batch, S = nframes + 1;
   // key mask -> valid-key counts (model/mdm.py:241-247; lengths_to_mask, data_loaders/tensors.py:3-6)
-  std::vector<int> kv(e->Bp, S);
+  // (host staging lives in the engine until the next call, so the asynchronous copies need no stream synchronisation)
+  std::vector<int>& kv = e->h_kv;
+  kv.assign(e->Bp, S);
   if (e->cfg.mask_frames && lengths_host && nframes > 1) {
     for (int b = 0; b < e->Bp; ++b) {
       long long len = lengths_host[b % B];
@@ -729,14 +813,14 @@ extern "C" int b200mdm_set_cond(b200mdm_engine* e, int32_t batch, int32_t nframe
   CUDA_TRY(cudaMemcpyAsync(e->kvlen, kv.data(), kv.size() * sizeof(int), cudaMemcpyHostToDevice, s));
   if (scale_dev) CUDA_TRY(cudaMemcpyAsync(e->scale, scale_dev, B * sizeof(float), cudaMemcpyDeviceToDevice, s));
   if (e->cfg.cond_mode == B200MDM_COND_ACTION && action_host) {
-    std::vector<int> a(B);
+    std::vector<int>& a = e->h_action;
+    a.assign(B, 0);
     for (int b = 0; b < B; ++b) {
       if (action_host[b] < 0 || action_host[b] >= e->cfg.num_actions) return fail(B200MDM_EINVAL, "action index out of range");
       a[b] = static_cast<int>(action_host[b]);
     }
     CUDA_TRY(cudaMemcpyAsync(e->action, a.data(), B * sizeof(int), cudaMemcpyHostToDevice, s));
   }
-  CUDA_TRY(cudaStreamSynchronize(s));  // host staging vectors go out of scope
   if (e->cfg.cond_mode == B200MDM_COND_TEXT && cond_embed_dev) {
     const size_t warps = static_cast<size_t>(B) * d;
     small_linear_kernel<0><<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, s>>>(cond_embed_dev, e->w_txt, e->b_txt, e->proj, B,
@@ -761,13 +845,11 @@ extern "C" int b200mdm_set_cond_dec(b200mdm_engine* e, int32_t batch, int32_t nf
   if (!e->finalized) return fail(B200MDM_ESTATE, "weights not finalised");
   if (batch <= 0 || nframes <= 0 || n_tokens <= 0 || n_tokens > 64) return fail(B200MDM_EINVAL, "bad batch / nframes / n_tokens (1..64)");
   if (nframes + e->ctx > e->cfg.pos_embed_max_len) return fail(B200MDM_EINVAL, "sequence longer than the positional table");
+  if (nframes + e->ctx > ATC_MAX_KEYS) return fail(B200MDM_ENOTIMPL, "sequences of more than %d tokens", ATC_MAX_KEYS);
   if (!enc_text_dev || !text_mask_host) return fail(B200MDM_EINVAL, "DiP needs y['text_embed'] = (tokens, mask)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int halves = scale_dev ? 2 : 1;
-  if (batch != e->B || nframes != e->T || halves != e->halves) {
-    CUDA_TRY(cudaDeviceSynchronize());
-    TRY(build_workspace(e, batch, nframes, halves));
-  }
+  TRY(select_workspace(e, batch, nframes, halves, s));
   const int d = e->d, B = batch, S = e->S, Bp = e->Bp, Mt = n_tokens, C = e->cfg.cond_dim;
   if (Mt != e->Mt) {
     CUDA_TRY(cudaDeviceSynchronize());
@@ -784,7 +866,8 @@ extern "C" int b200mdm_set_cond_dec(b200mdm_engine* e, int32_t batch, int32_t nf
     e->Mt = Mt;
   }
   // key mask of the frames: the context frames are always valid (model/mdm.py:204-206), then `lengths` frames of x
-  std::vector<int> kv(Bp, S);
+  std::vector<int>& kv = e->h_kv;
+  kv.assign(Bp, S);
   if (e->cfg.mask_frames && lengths_host && S > 1) {
     for (int b = 0; b < Bp; ++b) {
       long long len = lengths_host[b % B];
@@ -793,13 +876,13 @@ extern "C" int b200mdm_set_cond_dec(b200mdm_engine* e, int32_t batch, int32_t nf
       kv[b] = static_cast<int>(len) + e->ctx;
     }
   }
-  std::vector<unsigned char> mk(static_cast<size_t>(Bp) * Mt);
+  std::vector<unsigned char>& mk = e->h_mask;
+  mk.assign(static_cast<size_t>(Bp) * Mt, 0);
   for (int b = 0; b < Bp; ++b)
     for (int m = 0; m < Mt; ++m) mk[static_cast<size_t>(b) * Mt + m] = text_mask_host[static_cast<size_t>(b % B) * Mt + m] ? 1 : 0;
   CUDA_TRY(cudaMemcpyAsync(e->kvlen, kv.data(), kv.size() * sizeof(int), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(e->memmask, mk.data(), mk.size(), cudaMemcpyHostToDevice, s));
   if (scale_dev) CUDA_TRY(cudaMemcpyAsync(e->scale, scale_dev, B * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
   // text_emb = embed_text(mask_cond(enc_text)) per token (model/mdm.py:218), once per loop
   permute_mbc_kernel<<<dim3(Mt, B), 128, 0, s>>>(enc_text_dev, e->encperm, Mt, B, C);
   CUDA_TRY(cudaGetLastError());
@@ -846,6 +929,7 @@ struct StepArgs {
   float* x_out = nullptr;
   float* pred = nullptr;
   bool explicit_t = false;        // use e->tvec instead of timestep_map[state.cur]
+  bool philox = false;            // eps of this step is generated into e->eps_buf by the first kernel of the step
 };
 
 // Enqueue one denoiser forward (+ fused sampler step) on stream s.  Returns the number of kernels launched.
@@ -853,6 +937,13 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
   const int d = e->d, ff = e->ff, B = e->B, T = e->T, S = e->S, JF = e->JF, Kp = e->Kp_in;
   int nk = 0;
   PdlScope pdl_scope;
+  if (a.philox) {
+    const long long quads = (static_cast<long long>(JF) * T + 3) / 4 * B;
+    const int blocks = static_cast<int>(quads / 256 + 1 < 1184 ? quads / 256 + 1 : 1184);
+    CUDA_TRY(launch_k(philox_normal_kernel, dim3(blocks), dim3(256), 0, s, e->eps_buf, B, static_cast<long long>(JF) * T,
+                      0ull, 0ll, 0u, e->state));
+    ++nk;
+  }
   {
     dim3 grid((T + 31) / 32, (JF + 31) / 32, B), block(32, 8);
     CUDA_TRY(launch_k(pack_input_kernel, grid, block, 0, s, a.x_in, e->xin16, B, JF, T, S, Kp, 3 * Kp, e->s_off));
@@ -879,16 +970,17 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
   const bool wide = kw == 2;
   for (int l = 0; l < e->L; ++l) {
     const LayerW& w = e->layers[l];
-    {
-      EpiBiasF16<false>::Params p{w.bqkv};
-      TRY((launch_gemm2<EpiBiasF16<false>>(e->m_h16, w.m_wqkv, e->m_qkv_st, e->M, 3 * d, kw * d, p, s, e->num_sms)));
-    }
-    if (S <= ATC_MAX_KEYS) {
+    if (!wide && fused_qkv_enabled()) {
+      // QKV projection + attention in one kernel: the [M, 1536] qkv tensor never exists
+      TRY(launch_qkv_attention(e->m_h3, w.m_wqkv, w.m_wqkv_64, e->m_att_o, w.bqkv, e->kvlen, e->Bp, S, s, e->num_sms));
+      --nk;
+    } else {
+      {
+        EpiBiasF16<false>::Params p{w.bqkv};
+        TRY((launch_gemm2<EpiBiasF16<false>>(e->m_h16, w.m_wqkv, e->m_qkv_st, e->M, 3 * d, kw * d, p, s, e->num_sms)));
+      }
       AttnMaps am{e->m_att_q, e->m_att_kv, e->m_att_o};
       TRY(launch_attention_tc(am, e->kvlen, e->Bp, S, d, e->H, s, wide));
-    } else {
-      if (wide) return fail(B200MDM_ENOTIMPL, "trans_dec sequences longer than %d tokens", ATC_MAX_KEYS);
-      TRY(launch_attention_mma(e->qkv16, e->att16, e->kvlen, e->Bp, S, d, e->H, s));
     }
     TRY(launch_gemm_resid_ln(e->m_att, w.m_wo_256, e->m_res, e->M, kw * d, w.bo, w.g1, w.be1, s, e->num_sms));
     if (e->dec) {
@@ -979,7 +1071,7 @@ extern "C" int b200mdm_sample_step(b200mdm_engine* e, int32_t mode, int32_t inde
   if (index < 0 || index >= e->n_steps) return fail(B200MDM_EINVAL, "schedule index out of range");
   if (!x_t_dev || !noise_dev || !x_out_dev) return fail(B200MDM_EINVAL, "null tensor");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  step_set_kernel<<<1, 1, 0, s>>>(e->state, 0, index, nullptr, 0);
+  step_set_kernel<<<1, 1, 0, s>>>(e->state, 0, index, nullptr, 0, e->noise_seed, e->noise_sample_base);
   CUDA_TRY(cudaGetLastError());
   StepArgs a;
   a.mode = mode;
@@ -995,15 +1087,17 @@ extern "C" int b200mdm_sample_step(b200mdm_engine* e, int32_t mode, int32_t inde
   return B200MDM_OK;
 }
 
-extern "C" int b200mdm_sample_loop(b200mdm_engine* e, int32_t mode, int32_t skip_timesteps, const float* x_T_dev,
-                                   float* x_0_dev, const float* noise_tape_dev, int64_t noise_step_stride,
-                                   int32_t flags, int32_t use_graph, void* stream) {
+// Schedule indices first_index, first_index-1, ... (n_run of them) on the engine's working buffer.  x_in_dev == NULL
+// continues from the state the previous call left there; x_out_dev == NULL leaves the result there.
+extern "C" int b200mdm_sample_loop_range(b200mdm_engine* e, int32_t mode, int32_t first_index, int32_t n_run,
+                                         const float* x_in_dev, float* x_out_dev, const float* noise_tape_dev,
+                                         int64_t noise_step_stride, int32_t flags, int32_t use_graph, void* stream) {
   TRY(check_ready(e, true));
   if (mode != B200MDM_MODE_DDPM && mode != B200MDM_MODE_DDIM) return fail(B200MDM_EINVAL, "bad mode");
-  if (skip_timesteps < 0 || skip_timesteps >= e->n_steps) return fail(B200MDM_EINVAL, "bad skip_timesteps");
-  if (!x_T_dev || !x_0_dev || !noise_tape_dev) return fail(B200MDM_EINVAL, "null tensor");
+  if (n_run <= 0 || first_index >= e->n_steps || first_index - n_run + 1 < 0) return fail(B200MDM_EINVAL, "bad step range");
+  const bool philox = (flags & B200MDM_FLAG_PHILOX_NOISE) != 0;
+  if (!philox && !noise_tape_dev) return fail(B200MDM_EINVAL, "null noise tape (or pass B200MDM_FLAG_PHILOX_NOISE)");
   cudaStream_t user = static_cast<cudaStream_t>(stream);
-  const int n_run = e->n_steps - skip_timesteps;
   const size_t x_bytes = static_cast<size_t>(e->B) * e->JF * e->T * sizeof(float);
   // The loop runs in place on an engine-owned buffer (fixed address => the captured step graph never changes);
   // every element is read and written by the same thread of the fused output epilogue.
@@ -1011,7 +1105,8 @@ extern "C" int b200mdm_sample_loop(b200mdm_engine* e, int32_t mode, int32_t skip
   a.mode = mode;
   a.x_in = e->x_work;
   a.x_out = e->x_work;
-  a.noise = nullptr;
+  a.noise = philox ? e->eps_buf : nullptr;
+  a.philox = philox;
   a.const_noise = flags & B200MDM_FLAG_CONST_NOISE;
   a.clip = (flags & B200MDM_FLAG_CLIP_DENOISED) ? 1 : 0;
 
@@ -1051,8 +1146,8 @@ extern "C" int b200mdm_sample_loop(b200mdm_engine* e, int32_t mode, int32_t skip
     CUDA_TRY(cudaEventRecord(e->ev_in, user));
     CUDA_TRY(cudaStreamWaitEvent(e->work, e->ev_in, 0));
   }
-  CUDA_TRY(cudaMemcpyAsync(e->x_work, x_T_dev, x_bytes, cudaMemcpyDeviceToDevice, s));
-  step_set_kernel<<<1, 1, 0, s>>>(e->state, 0, n_run - 1, noise_tape_dev, noise_step_stride);
+  if (x_in_dev) CUDA_TRY(cudaMemcpyAsync(e->x_work, x_in_dev, x_bytes, cudaMemcpyDeviceToDevice, s));
+  step_set_kernel<<<1, 1, 0, s>>>(e->state, 0, first_index, noise_tape_dev, noise_step_stride, e->noise_seed, e->noise_sample_base);
   CUDA_TRY(cudaGetLastError());
   e->launches += 1;
   if (use_graph) {
@@ -1069,11 +1164,40 @@ extern "C" int b200mdm_sample_loop(b200mdm_engine* e, int32_t mode, int32_t skip
       e->launches += nk + 1;
     }
   }
-  CUDA_TRY(cudaMemcpyAsync(x_0_dev, e->x_work, x_bytes, cudaMemcpyDeviceToDevice, s));
+  if (x_out_dev) CUDA_TRY(cudaMemcpyAsync(x_out_dev, e->x_work, x_bytes, cudaMemcpyDeviceToDevice, s));
   if (use_graph) {
     CUDA_TRY(cudaEventRecord(e->ev_out, e->work));
     CUDA_TRY(cudaStreamWaitEvent(user, e->ev_out, 0));
   }
+  return B200MDM_OK;
+}
+
+extern "C" int b200mdm_sample_loop(b200mdm_engine* e, int32_t mode, int32_t skip_timesteps, const float* x_T_dev,
+                                   float* x_0_dev, const float* noise_tape_dev, int64_t noise_step_stride,
+                                   int32_t flags, int32_t use_graph, void* stream) {
+  TRY(check_ready(e, true));
+  if (skip_timesteps < 0 || skip_timesteps >= e->n_steps) return fail(B200MDM_EINVAL, "bad skip_timesteps");
+  if (!x_T_dev || !x_0_dev) return fail(B200MDM_EINVAL, "null tensor");
+  return b200mdm_sample_loop_range(e, mode, e->n_steps - 1 - skip_timesteps, e->n_steps - skip_timesteps, x_T_dev, x_0_dev,
+                                   noise_tape_dev, noise_step_stride, flags, use_graph, stream);
+}
+
+// Counter-based noise stream of the engine (Philox4x32-10 + Box-Muller, kernels.cuh): eps of schedule index i for
+// global sample g depends on (seed, i, g, element) only -- not on the batch split, the GPU count or the chunking.
+extern "C" int b200mdm_set_noise_stream(b200mdm_engine* e, uint64_t seed, int64_t sample_index_base) {
+  if (!e) return fail(B200MDM_EINVAL, "null engine");
+  e->noise_seed = seed;
+  e->noise_sample_base = sample_index_base;
+  return B200MDM_OK;
+}
+extern "C" int b200mdm_philox_normal(float* out_dev, int32_t batch, int64_t n_per_sample, uint64_t seed,
+                                     int64_t sample_index_base, int32_t step_id, void* stream) {
+  if (!out_dev || batch <= 0 || n_per_sample <= 0) return fail(B200MDM_EINVAL, "bad argument");
+  const long long quads = (n_per_sample + 3) / 4 * batch;
+  const int blocks = static_cast<int>(quads / 256 + 1 < 1184 ? quads / 256 + 1 : 1184);
+  philox_normal_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(out_dev, batch, n_per_sample, seed, sample_index_base,
+                                                                             static_cast<uint32_t>(step_id), nullptr);
+  CUDA_TRY(cudaGetLastError());
   return B200MDM_OK;
 }
 
@@ -1131,11 +1255,8 @@ extern "C" int b200mdm_test_gemm_f16(const void* a16_dev, const void* w16_dev, c
     EpiBiasF16<false>::Params p{bias_dev};
     return launch_gemm2<EpiBiasF16<false>>(ma, mb, mc, M, N, K, p, s, sms);
   }
-  switch (block_n) {
-    case 256: return test_gemm_bn<256>(a16_dev, w16_dev, bias_dev, out16_dev, M, N, K, act, s, sms);
-    case 128: return test_gemm_bn<128>(a16_dev, w16_dev, bias_dev, out16_dev, M, N, K, act, s, sms);
-    default: return fail(B200MDM_EINVAL, "block_n must be 512 (CTA pair), 256 or 128");
-  }
+  if (block_n == 128) return test_gemm_bn<128>(a16_dev, w16_dev, bias_dev, out16_dev, M, N, K, act, s, sms);
+  return fail(B200MDM_EINVAL, "block_n must be 512 (CTA pair) or 128 (single CTA)");
 }
 
 extern "C" int b200mdm_test_attention(const void* qkv16_dev, void* out16_dev, const int32_t* kvlen_dev,
@@ -1143,14 +1264,28 @@ extern "C" int b200mdm_test_attention(const void* qkv16_dev, void* out16_dev, co
   if (!qkv16_dev || !out16_dev || !kvlen_dev || n_samples <= 0 || S <= 0) return fail(B200MDM_EINVAL, "bad argument");
   TRY(init_kernel_attrs());
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (impl == 0) {
-    if (S > ATC_MAX_KEYS) return fail(B200MDM_EINVAL, "tcgen05 attention handles at most %d tokens", ATC_MAX_KEYS);
-    AttnMaps am;
-    TRY(make_attn_maps(&am, static_cast<const __half*>(qkv16_dev), static_cast<__half*>(out16_dev), n_samples, S, d));
-    return launch_attention_tc(am, kvlen_dev, n_samples, S, d, d / ATC_DH, s);
-  }
-  return launch_attention_mma(static_cast<const __half*>(qkv16_dev), static_cast<__half*>(out16_dev), kvlen_dev, n_samples,
-                              S, d, d / ATT_DH, s);
+  if (impl != 0) return fail(B200MDM_EINVAL, "impl 0 (tcgen05) is the only attention kernel");
+  if (S > ATC_MAX_KEYS) return fail(B200MDM_EINVAL, "tcgen05 attention handles at most %d tokens", ATC_MAX_KEYS);
+  AttnMaps am;
+  TRY(make_attn_maps(&am, static_cast<const __half*>(qkv16_dev), static_cast<__half*>(out16_dev), n_samples, S, d));
+  return launch_attention_tc(am, kvlen_dev, n_samples, S, d, d / ATC_DH, s);
+}
+
+extern "C" int b200mdm_test_qkv_attention(const void* h16_dev, int32_t ld, const void* wqkv16_dev, const float* bqkv_dev,
+                                          void* out16_dev, const int32_t* kvlen_dev, int32_t n_samples, int32_t S,
+                                          void* stream) {
+  if (!h16_dev || !wqkv16_dev || !bqkv_dev || !out16_dev || !kvlen_dev || n_samples <= 0 || S <= 0 || S > 256 || ld < 512 || ld % 8)
+    return fail(B200MDM_EINVAL, "bad argument");
+  TRY(init_kernel_attrs());
+  int dev = 0, sms = 148;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CUtensorMap mh, mw128, mw64, mo;
+  TRY(make_map_3d(&mh, h16_dev, n_samples, S, 512, ld, 128));
+  TRY(make_map(&mw128, wqkv16_dev, 1536, 512, 512, 128));
+  TRY(make_map(&mw64, wqkv16_dev, 1536, 512, 512, 64));
+  TRY(make_map_3d(&mo, out16_dev, n_samples, S, 512, 512, 32));
+  return launch_qkv_attention(mh, mw128, mw64, mo, bqkv_dev, kvlen_dev, n_samples, S, static_cast<cudaStream_t>(stream), sms);
 }
 
 extern "C" int b200mdm_test_gemm_resid_ln(const void* a16_dev, const void* w16_dev, const float* bias_dev,
@@ -1174,12 +1309,6 @@ extern "C" int b200mdm_test_gemm_resid_ln(const void* a16_dev, const void* w16_d
 extern "C" int b200mdm_debug_trace(long long* dev_buf) {
   CUDA_TRY(cudaMemcpyToSymbol(g_gemm2_trace, &dev_buf, sizeof(dev_buf)));
   return B200MDM_OK;
-}
-
-extern "C" int b200mdm_test_layernorm(float* h32_dev, void* h16_dev, const float* gamma_dev, const float* beta_dev,
-                                      int32_t M, void* stream) {
-  if (!h32_dev || !h16_dev || !gamma_dev || !beta_dev || M <= 0) return fail(B200MDM_EINVAL, "bad argument");
-  return launch_layernorm(h32_dev, static_cast<__half*>(h16_dev), gamma_dev, beta_dev, M, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------------------ post-processing

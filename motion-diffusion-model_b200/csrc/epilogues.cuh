@@ -216,71 +216,6 @@ struct EpiBiasF16Wide {
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// h32[row, col] += acc + bias[col]      (fp32 residual add in place; kept for the GEMM unit tests -- the engine's
-// residual + LayerNorm epilogue lives in gemm_ln.cuh).
-// Per 32-column chunk: TMA load of the residual slab (issued one chunk ahead, three rotating buffers), add in
-// registers, write back into the same slab, TMA store.  map_c: fp32 [M, N], box {32 cols, 32 rows}, SWIZZLE_128B.
-struct EpiResidualF32 {
-  static constexpr int NBUF = 2;
-  static constexpr int SMEM_PER_WARP = NBUF * 4096;  // two residual/output slabs
-  static constexpr bool RELEASE_EARLY = true;
-  struct Params {
-    const float* bias;
-  };
-  static __device__ __forceinline__ void prefetch(EpiCtx& ctx, uint32_t seq, int row0, int col0) {
-    // buffer seq % NBUF was last stored from NBUF chunks ago: with two buffers that is the most recent store
-    if (ctx.lane == 0) {
-      bulk_wait_group_read<0>();
-      const uint32_t b = seq % NBUF;
-      mbar_expect_tx(&ctx.bars[b], 4096);
-      tma_load_2d(ctx.smem + b * 4096, ctx.map_c, &ctx.bars[b], col0, row0);
-    }
-  }
-  static __device__ __forceinline__ void tile_begin(EpiCtx& ctx, const Params& p, int row0, int col_base) {
-    // NOTE: tile_begin does not know which column block this warp starts with; chunk() of the first chunk issues it
-  }
-  static __device__ __forceinline__ void preload(const Params& p, float* dst, int N, int tid, int nthreads) {
-    for (int i = tid; i < N; i += nthreads) dst[i] = p.bias[i];
-  }
-  static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0,
-                                               int next_col0) {
-    const uint32_t b = ctx.seq % NBUF;
-    if (!ctx.primed) {  // first chunk of this warp in the tile: nothing was prefetched yet
-      prefetch(ctx, ctx.seq, row0, col0);
-      ctx.primed = true;
-    }
-    if (next_col0 >= 0) prefetch(ctx, ctx.seq + 1, row0, next_col0); else ctx.primed = false;
-    uint8_t* slab = ctx.smem + b * 4096;
-    const float* bs = ctx.bias_all + col0;
-    mbar_wait(&ctx.bars[b], (ctx.seq / NBUF) & 1);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4* cell = reinterpret_cast<float4*>(slab + slab_off(ctx.lane, j));
-      const float4 r = *cell;
-      const float4 bb = *reinterpret_cast<const float4*>(bs + 4 * j);
-      float4 o;
-      o.x = r.x + (__uint_as_float(raw[4 * j + 0]) + bb.x);
-      o.y = r.y + (__uint_as_float(raw[4 * j + 1]) + bb.y);
-      o.z = r.z + (__uint_as_float(raw[4 * j + 2]) + bb.z);
-      o.w = r.w + (__uint_as_float(raw[4 * j + 3]) + bb.w);
-      *cell = o;
-    }
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (ctx.lane == 0) {
-      tma_store_2d(ctx.map_c, slab, col0, row0);
-      bulk_commit_group();
-    }
-    ctx.seq++;
-  }
-  static __device__ __forceinline__ void tile_end(EpiCtx&, const Params&, int, int, uint32_t) {}
-  static __device__ __forceinline__ void finish(EpiCtx& ctx) {
-    if (ctx.lane == 0) bulk_wait_group<0>();
-    __syncwarp();
-  }
-};
-
-// ---------------------------------------------------------------------------------------------------------
 // InputProcess + positional encoding (reference model/mdm.py:238,252,343-349):
 //   GEMM rows are (b, s) over B*S, s >= 1 is frame s-1:  h = acc + (bias + pe[s]).  The frame rows are identical for
 //   the cond / uncond halves of the packed CFG batch, so every slab is TMA-stored twice (one tensor map per half --
@@ -356,6 +291,8 @@ struct StepState {
   int pad;
   const float* noise;            // loop mode: base of the noise tape (set per loop, so the step graph is reusable)
   long long noise_step_stride;   // loop mode: elements between consecutive steps of the tape
+  unsigned long long seed;       // in-engine Philox noise (philox_normal_kernel): stream seed ...
+  long long sample_base;         // ... and the global index of this workspace's sample 0
 };
 
 struct EpiOutStep {

@@ -76,56 +76,72 @@ __global__ void step_advance_kernel(StepState* state) {
   state->done += 1;
   state->cur -= 1;
 }
-__global__ void step_set_kernel(StepState* state, int done, int cur, const float* noise, long long noise_step_stride) {
+__global__ void step_set_kernel(StepState* state, int done, int cur, const float* noise, long long noise_step_stride,
+                                unsigned long long seed, long long sample_base) {
   state->done = done;
   state->cur = cur;
   state->start = cur;
   state->noise = noise;
   state->noise_step_stride = noise_step_stride;
+  state->seed = seed;
+  state->sample_base = sample_base;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// In-place LayerNorm over rows of h32 [M, 512] (eps 1e-5, biased variance, two-pass like ATen) + fp16 copy.
-// One warp per row; 512 = 32 lanes x 4 float4.
-__global__ void layernorm512_kernel(float* __restrict__ h32, __half* __restrict__ h16, const float* __restrict__ gamma,
-                                    const float* __restrict__ beta, int M, float eps) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  float4* p = reinterpret_cast<float4*>(h32 + static_cast<size_t>(row) * 512);
-  float4 v[4];
-  float sum = 0.f;
+// The engine's own noise stream (B200MDM_FLAG_PHILOX_NOISE / b200mdm_philox_normal): replaces the reference's
+// th.randn_like(x) per step (diffusion/gaussian_diffusion.py:525, :770) when the caller asks for a stream that does not
+// depend on how the batch is split over GPUs or on how many steps are drawn at once.
+//   Philox4x32-10 (Salmon et al., SC'11), key = (seed_lo, seed_hi),
+//   counter = (q, step_id, g_lo, g_hi ^ 0x4d444d42)   q = element index / 4 inside the sample, g = global sample index
+//   the 4 output words w0..w3 -> u_k = ((w_k >> 8) + 0.5) * 2^-24 in (0, 1);
+//   elements 4q..4q+3 = r0 cos(2 pi u1), r0 sin(2 pi u1), r1 cos(2 pi u3), r1 sin(2 pi u3),  r0 = sqrt(-2 ln u0), r1 = sqrt(-2 ln u2)
+// step_id = schedule index of the step that consumes the eps (state->cur when `state` != nullptr); x_T uses 0xffffffff.
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    v[i] = p[lane + 32 * i];
-    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum * (1.f / 512.f);
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-    sq += (a * a + b * b) + (c * c + d * d);
+}
+__global__ void philox_normal_kernel(float* __restrict__ out, int B, long long n, unsigned long long seed,
+                                     long long sample_base, uint32_t step_id, const StepState* __restrict__ state) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (state != nullptr) {
+    seed = state->seed;
+    sample_base = state->sample_base;
+    step_id = static_cast<uint32_t>(state->cur);
   }
+  const long long qn = (n + 3) / 4, total = qn * B;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / qn, q = i - b * qn;
+    const unsigned long long g = static_cast<unsigned long long>(sample_base + b);
+    uint32_t c[4] = {static_cast<uint32_t>(q), step_id, static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32) ^ 0x4d444d42u};
+    philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    float z[4];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq * (1.f / 512.f) + eps);
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(beta);
-  __half2* q = reinterpret_cast<__half2*>(h16 + static_cast<size_t>(row) * 512);
+    for (int h = 0; h < 2; ++h) {
+      const float u0 = (static_cast<float>(c[2 * h] >> 8) + 0.5f) * 5.9604644775390625e-08f;
+      const float u1 = (static_cast<float>(c[2 * h + 1] >> 8) + 0.5f) * 5.9604644775390625e-08f;
+      const float r = sqrtf(-2.0f * logf(u0));
+      float sn, cs;
+      sincospif(2.0f * u1, &sn, &cs);
+      z[2 * h] = r * cs;
+      z[2 * h + 1] = r * sn;
+    }
+    float* dst = out + b * n + 4 * q;
+    if (4 * q + 3 < n && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      *reinterpret_cast<float4*>(dst) = make_float4(z[0], z[1], z[2], z[3]);
+    } else {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 g = g4[lane + 32 * i], be = b4[lane + 32 * i];
-    float4 o;
-    o.x = (v[i].x - mean) * rstd * g.x + be.x;
-    o.y = (v[i].y - mean) * rstd * g.y + be.y;
-    o.z = (v[i].z - mean) * rstd * g.z + be.z;
-    o.w = (v[i].w - mean) * rstd * g.w + be.w;
-    p[lane + 32 * i] = o;
-    q[2 * (lane + 32 * i)] = __floats2half2_rn(o.x, o.y);
-    q[2 * (lane + 32 * i) + 1] = __floats2half2_rn(o.z, o.w);
+      for (int j = 0; j < 4; ++j)
+        if (4 * q + j < n) dst[j] = z[j];
+    }
   }
 }
 

@@ -37,17 +37,63 @@ def _repeat_y(y, times):
 
 def _draw_noise(repeats, chunks, n_steps, shape, device):
     """x_T and eps for `repeats` sequential reference calls, each of `chunks` diffusion loops (1, or the autoregressive
-    chunk count), in the order the reference would draw them; stacked along the batch."""
-    xs = [[None] * repeats for _ in range(chunks)]
-    es = [[None] * repeats for _ in range(chunks)]
+    chunk count), in the order the reference would draw them; stacked along the batch, written straight into ONE
+    preallocated pair of tensors (no stack / cat copies)."""
+    B = shape[0]
+    noise = torch.empty((chunks, repeats * B) + tuple(shape[1:]), device=device)
+    tape = torch.empty((chunks, n_steps, repeats * B) + tuple(shape[1:]), device=device)
     for t in range(repeats):
         for c in range(chunks):
-            x = torch.randn(*shape, device=device)
-            xs[c][t] = x
-            es[c][t] = torch.stack([torch.randn_like(x) for _ in range(n_steps)])
-    noise = torch.stack([torch.cat(xs[c], dim=0) for c in range(chunks)])            # [chunks, repeats*B, ...]
-    tape = torch.stack([torch.cat(es[c], dim=1) for c in range(chunks)])             # [chunks, n_steps, repeats*B, ...]
+            noise[c, t * B:(t + 1) * B] = torch.randn(*shape, device=device)
+            for k in range(n_steps):
+                tape[c, k, t * B:(t + 1) * B].normal_()
     return noise, tape
+
+
+# A stacked multimodality batch is only worth it while its noise fits: the tape of ONE repeat of the reference's
+# mm_short evaluation (bs 32, 263 x 196, 1000 steps) is 6.6 GB.
+TAPE_BUDGET_BYTES = 8 << 30
+
+
+class _RepeatStreams:
+    """The generator streams of `repeats` SEQUENTIAL reference calls, readable in any interleaving.
+
+    The reference runs repeat r's whole loop (x_T, then one randn_like per step) before repeat r+1 starts, all from
+    torch's default generator.  Drawing repeat r's k-th eps before repeat r-1 has finished needs a generator positioned
+    at `offset_0 + r * (n_steps + 1) * delta`, where delta is what one randn of this shape advances the Philox offset
+    by (measured, not assumed).  One cloned generator per repeat provides exactly that; the default generator is left
+    where the sequential calls would have left it."""
+
+    def __init__(self, repeats, n_steps, shape, device):
+        main = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+        probe = main.clone_state()
+        o0 = probe.get_offset()
+        torch.randn(*shape, device=device, generator=probe)
+        delta = probe.get_offset() - o0
+        self.gens = []
+        for r in range(repeats):
+            g = main.clone_state()
+            g.set_offset(main.get_offset() + r * (n_steps + 1) * delta)
+            self.gens.append(g)
+        main.set_offset(main.get_offset() + repeats * (n_steps + 1) * delta)
+        self.B, self.shape, self.device = shape[0], tuple(shape), device
+
+    def x_T(self):
+        return torch.cat([torch.randn(*self.shape, device=self.device, generator=g) for g in self.gens], dim=0)
+
+    def fill(self, buf, k0):                                   # buf [n, repeats*B, ...]: eps of steps k0 .. k0+n-1
+        for j in range(buf.shape[0]):
+            for r, g in enumerate(self.gens):
+                buf[j, r * self.B:(r + 1) * self.B].normal_(generator=g)
+
+
+def _offset_api(device):
+    try:
+        g = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+        g.clone_state().get_offset()
+        return True
+    except Exception:
+        return False
 
 
 class CompMDMGeneratedDataset(Dataset):
@@ -98,15 +144,37 @@ class CompMDMGeneratedDataset(Dataset):
                     draw_shape = shape[:-1] + (args.pred_len,)
                 else:
                     chunks, draw_shape = 1, shape
-                noise, tape = _draw_noise(repeat_times, chunks, n_steps, draw_shape, device)
-                ys = _repeat_y({k: v for k, v in y.items() if k != "text"}, repeat_times)
-                kw = dict(clip_denoised=clip_denoised, model_kwargs={"y": ys}, skip_timesteps=0, init_image=None,
-                          progress=False, dump_steps=None, const_noise=False)
-                stacked_shape = (repeat_times * shape[0],) + shape[1:]
-                if autoregressive:
-                    sample = sample_fn(model, stacked_shape, noise=noise, noise_tape=tape, **kw)
+                ys_full = {k: v for k, v in y.items() if k != "text"}
+                kw = dict(clip_denoised=clip_denoised, skip_timesteps=0, init_image=None, progress=False, dump_steps=None,
+                          const_noise=False)
+                per_repeat = 4 * n_steps * chunks * int(np.prod(draw_shape))
+                if repeat_times * per_repeat <= TAPE_BUDGET_BYTES or autoregressive:
+                    # small enough: all repeats in one loop, noise drawn up front in the reference's order
+                    noise, tape = _draw_noise(repeat_times, chunks, n_steps, draw_shape, device)
+                    stacked_shape = (repeat_times * shape[0],) + shape[1:]
+                    kw["model_kwargs"] = {"y": _repeat_y(ys_full, repeat_times)}
+                    if autoregressive:
+                        sample = sample_fn(model, stacked_shape, noise=noise, noise_tape=tape, **kw)
+                    else:
+                        sample = sample_fn(model, stacked_shape, noise=noise[0], noise_tape=tape[0], **kw)
+                elif device.type == "cuda" and _offset_api(device):
+                    # long loops (1000 steps): still ONE stacked loop, eps produced chunk by chunk from per-repeat
+                    # generator clones positioned where the reference's sequential calls would be
+                    streams = _RepeatStreams(repeat_times, n_steps, draw_shape, device)
+                    stacked_shape = (repeat_times * shape[0],) + shape[1:]
+                    kw["model_kwargs"] = {"y": _repeat_y(ys_full, repeat_times)}
+                    sample = sample_fn(model, stacked_shape, noise=streams.x_T(), noise_fn=streams.fill, **kw)
                 else:
-                    sample = sample_fn(model, stacked_shape, noise=noise[0], noise_tape=tape[0], **kw)
+                    # no offset API: groups of repeats sized by the budget, sequential like the reference
+                    group = max(1, int(TAPE_BUDGET_BYTES // per_repeat))
+                    parts = []
+                    for r0 in range(0, repeat_times, group):
+                        g = min(group, repeat_times - r0)
+                        noise, tape = _draw_noise(g, 1, n_steps, draw_shape, device)
+                        kw["model_kwargs"] = {"y": _repeat_y(ys_full, g)}
+                        parts.append(sample_fn(model, (g * shape[0],) + shape[1:], noise=noise[0], noise_tape=tape[0], **kw))
+                        del noise, tape
+                    sample = torch.cat(parts, dim=0)
                 if "prefix" in y:                                      # :216-217
                     y["lengths"] = y["orig_lengths"]
                 sample = sample.reshape(repeat_times, shape[0], *sample.shape[1:])

@@ -182,14 +182,62 @@ class GaussianDiffusion:
                                init_image.to(device=device, dtype=torch.float32).contiguous(), img.contiguous())
         return img.contiguous()
 
-    @staticmethod
-    def _draw_tape(n_run, img):
-        """Per-step eps, drawn with the same generator calls, in the same order, as the reference's
-        `th.randn_like(x)` at every step (:525 / :770) -- so a seeded run consumes the identical stream."""
-        tape = torch.empty((n_run,) + tuple(img.shape), device=img.device, dtype=torch.float32)
-        for k in range(n_run):
-            tape[k] = torch.randn_like(img)
-        return tape
+    # Steps of per-step eps drawn ahead of the loop at a time.  The reference draws `th.randn_like(x)` inside every step
+    # (:525 / :770); materialising all of them up front costs n_steps x |x| (13.2 GB at 1000 steps, B = 64).  Instead the
+    # draws are made -- by the same generator calls in the same order, so a seeded run consumes the identical stream --
+    # NOISE_CHUNK steps at a time on a side stream into three rotating buffers, while the engine runs the previous chunk.
+    NOISE_CHUNK = 16
+
+    def _run_generator_loop(self, eng, mode, img, n_run, first, flags, use_graph, noise_fn=None):
+        """noise_fn(buf, k0): fill buf[j] with the eps of the (k0+j)-th executed step, j < len(buf) (runs on the side
+        stream); default = one `normal_()` per step from torch's default generator."""
+        dev = img.device
+        chunk = max(1, min(self.NOISE_CHUNK, n_run))
+        nbuf = 3 if n_run > 2 * chunk else (2 if n_run > chunk else 1)
+        bufs = [torch.empty((chunk,) + tuple(img.shape), device=dev, dtype=torch.float32) for _ in range(nbuf)]
+        out = torch.empty_like(img)
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev)
+        side.wait_stream(main)                       # x_T (and the buffers) were produced on the caller's stream
+        ready = [torch.cuda.Event() for _ in range(nbuf)]
+        free = [None] * nbuf
+        n_chunks = (n_run + chunk - 1) // chunk
+
+        def draw(c):
+            b, n = c % nbuf, min(chunk, n_run - c * chunk)
+            with torch.cuda.stream(side):
+                if free[b] is not None:
+                    side.wait_event(free[b])         # the loop chunk that last read this buffer has finished
+                if noise_fn is not None:
+                    noise_fn(bufs[b][:n], c * chunk)
+                else:
+                    for k in range(n):
+                        bufs[b][k].normal_()         # == th.randn_like(x): same generator, same call order
+                ready[b].record(side)
+
+        draw(0)
+        done = 0
+        for c in range(n_chunks):
+            if c + 1 < n_chunks:
+                draw(c + 1)                          # overlaps loop chunk c-1 / c on the engine stream
+            b, n = c % nbuf, min(chunk, n_run - c * chunk)
+            main.wait_event(ready[b])
+            eng.sample_loop_range(mode, first - done, n, img if c == 0 else None, out if c == n_chunks - 1 else None,
+                                  bufs[b], flags, use_graph)
+            free[b] = torch.cuda.Event()
+            free[b].record(main)                     # main has been made to wait for the engine stream by the call
+            done += n
+        eng._keep["loop"] = (img, bufs)
+        return out
+
+    _side_streams = {}
+
+    @classmethod
+    def _side_stream(cls, dev):
+        key = (dev.type, dev.index)
+        if key not in cls._side_streams:
+            cls._side_streams[key] = torch.cuda.Stream(device=dev)
+        return cls._side_streams[key]
 
     # ------------------------------------------------------------------ DDPM
     def q_sample(self, x_start, t, noise=None):
@@ -203,33 +251,49 @@ class GaussianDiffusion:
     def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                       model_kwargs=None, device=None, progress=False, skip_timesteps=0, init_image=None,
                       randomize_class=False, cond_fn_with_grad=False, dump_steps=None, const_noise=False,
-                      noise_tape=None, use_graph=True):
+                      noise_tape=None, use_graph=True, noise_seed=None, sample_index_base=0, noise_fn=None):
         """reference gaussian_diffusion.py:591-658.  Extra (optional) keywords: `noise_tape` [n_run, *shape]
-        replaces the generator draws (parity tests / multi-GPU slicing); `use_graph` toggles CUDA-graph replay."""
+        replaces the generator draws (parity tests); `noise_seed` (+ `sample_index_base`) switches x_T and every eps to
+        the engine's counter-based Philox stream (no tape, independent of the batch split -- parallel.py);
+        `use_graph` toggles CUDA-graph replay; `noise_fn(buf, k0)` fills eps chunks on demand (evaluation caller).
+        Default: torch's generator, the reference's draw order, drawn in chunks of NOISE_CHUNK steps."""
         return self._loop(_lib.MODE_DDPM, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device,
                           skip_timesteps, init_image, randomize_class, cond_fn_with_grad, dump_steps, const_noise,
-                          0.0, noise_tape, use_graph)
+                          0.0, noise_tape, use_graph, noise_seed, sample_index_base, noise_fn)
 
     def _loop(self, mode, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device, skip_timesteps,
-              init_image, randomize_class, cond_fn_with_grad, dump_steps, const_noise, eta, noise_tape, use_graph):
+              init_image, randomize_class, cond_fn_with_grad, dump_steps, const_noise, eta, noise_tape, use_graph,
+              noise_seed=None, sample_index_base=0, noise_fn=None):
         self._reject_hooks(denoised_fn, cond_fn, randomize_class, cond_fn_with_grad)
         assert isinstance(shape, (tuple, list))
         if device is None:
             device = next(model.parameters()).device
         eng = self._prepare(model, shape, model_kwargs, device, eta)
+        if noise_seed is not None and noise is None:
+            noise = eng.philox_normal(shape, noise_seed, sample_index_base, -1, device)     # x_T from the engine stream
         img = self._initial(eng, shape, noise, device, skip_timesteps, init_image)
         n_run = self.num_timesteps - skip_timesteps
-        tape = noise_tape if noise_tape is not None else self._draw_tape(n_run, img)
-        tape = tape.to(device=device, dtype=torch.float32).contiguous()
-        assert tape.shape[0] == n_run and tuple(tape.shape[1:]) == tuple(img.shape), (tape.shape, img.shape)
+        first = n_run - 1
         flags = (1 if const_noise else 0) | (2 if clip_denoised else 0)
+        if noise_seed is not None:                   # engine-side counter-based eps: no tape at all
+            assert noise_tape is None and dump_steps is None, "noise_seed excludes noise_tape / dump_steps"
+            eng.set_noise_stream(noise_seed, sample_index_base)
+            out = torch.empty_like(img)
+            eng.sample_loop_range(mode, first, n_run, img, out, None, flags, use_graph)
+            eng._keep["loop"] = (img,)
+            return out
         if dump_steps is not None:                   # :655-657 -- needs the intermediate samples
             dump = []
             for k in range(n_run):
-                img, _ = eng.sample_step(mode, n_run - 1 - k, img, tape[k], flags, want_pred=False)
+                eps = noise_tape[k].to(device=device, dtype=torch.float32) if noise_tape is not None else torch.randn_like(img)
+                img, _ = eng.sample_step(mode, n_run - 1 - k, img, eps, flags, want_pred=False)
                 if k in dump_steps:
                     dump.append(img.clone())
             return dump
+        if noise_tape is None:
+            return self._run_generator_loop(eng, mode, img, n_run, first, flags, use_graph, noise_fn)
+        tape = noise_tape.to(device=device, dtype=torch.float32).contiguous()
+        assert tape.shape[0] == n_run and tuple(tape.shape[1:]) == tuple(img.shape), (tape.shape, img.shape)
         return eng.sample_loop(mode, img, tape, skip_timesteps, flags, use_graph)
 
     def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
@@ -278,7 +342,7 @@ class GaussianDiffusion:
     def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                          model_kwargs=None, device=None, progress=False, eta=0.0, skip_timesteps=0, init_image=None,
                          randomize_class=False, cond_fn_with_grad=False, dump_steps=None, const_noise=False,
-                         noise_tape=None, use_graph=True):
+                         noise_tape=None, use_graph=True, noise_seed=None, sample_index_base=0):
         """reference gaussian_diffusion.py:876-923 (raises on dump_steps / const_noise exactly like it, :900-903;
         note the reference does NOT cache the text embedding on this path -- we do, the result is identical)."""
         if dump_steps is not None:
@@ -287,7 +351,7 @@ class GaussianDiffusion:
             raise NotImplementedError()
         return self._loop(_lib.MODE_DDIM, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device,
                           skip_timesteps, init_image, randomize_class, cond_fn_with_grad, None, False, eta, noise_tape,
-                          use_graph)
+                          use_graph, noise_seed, sample_index_base)
 
     def ddim_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                                      model_kwargs=None, device=None, progress=False, eta=0.0, skip_timesteps=0,

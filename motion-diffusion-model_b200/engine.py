@@ -204,9 +204,30 @@ class Engine:
         out = torch.empty_like(x)
         check(self.lib.b200mdm_sample_loop(self.h, mode, skip_timesteps, _ptr(x), _ptr(out), _ptr(tape), tape.stride(0),
                                            flags, int(use_graph), _stream()))
-        # the loop is asynchronous and runs on the engine stream: keep its inputs alive and tell the caching
-        # allocator that another stream is using them
+        # the loop is asynchronous and runs on the engine's own stream, which torch's caching allocator knows nothing
+        # about: the inputs are kept referenced here until the next loop replaces them
         self._keep["loop"] = (x, tape)
+        return out
+
+    def sample_loop_range(self, mode, first_index, n_run, x_in, x_out, tape, flags=0, use_graph=True):
+        """Steps first_index .. first_index-n_run+1 on the engine's working buffer (b200mdm_sample_loop_range).
+        x_in None: continue; x_out None: leave the state in the engine; tape None: B200MDM_FLAG_PHILOX_NOISE."""
+        if tape is not None:
+            assert tape.is_contiguous() and tape.dtype == torch.float32 and tape.shape[0] >= n_run
+        else:
+            flags |= _lib.FLAG_PHILOX_NOISE
+        check(self.lib.b200mdm_sample_loop_range(self.h, mode, first_index, n_run, _ptr(x_in), _ptr(x_out), _ptr(tape),
+                                                 tape.stride(0) if tape is not None else 0, flags, int(use_graph), _stream()))
+
+    def set_noise_stream(self, seed, sample_index_base=0):
+        check(self.lib.b200mdm_set_noise_stream(self.h, ctypes.c_uint64(int(seed) & (2 ** 64 - 1)), int(sample_index_base)))
+
+    def philox_normal(self, shape, seed, sample_index_base, step_id, device):
+        """[B, ...] fp32 from the engine's counter-based stream (x_T: step_id = -1)."""
+        out = torch.empty(tuple(shape), device=device, dtype=torch.float32)
+        n = out[0].numel()
+        check(self.lib.b200mdm_philox_normal(_ptr(out), int(shape[0]), n, ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
+                                             int(sample_index_base), int(step_id), _stream()))
         return out
 
     def q_sample(self, sqrt_ac, sqrt_1mac, x_start, noise):

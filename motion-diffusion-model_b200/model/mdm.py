@@ -219,13 +219,22 @@ def _run_model(model, x, timesteps, y, guided):
 
 
 def engine_for(model):
-    """(engine, guided) for a bare MDM or a ClassifierFreeSampleModel wrapper (possibly behind _WrappedModel)."""
+    """(engine, guided) for a bare MDM or a ClassifierFreeSampleModel wrapper (possibly behind respace._WrappedModel).
+
+    Only wrappers this package knows are looked through: an unknown object that merely has a `.model` attribute (for
+    instance a guidance wrapper class from another import of this package, or the reference's own
+    ClassifierFreeSampleModel) would otherwise be unwrapped down to the bare denoiser and sampled WITHOUT guidance,
+    silently."""
     from ..utils.sampler_util import ClassifierFreeSampleModel
+    from ..diffusion.respace import _WrappedModel
     inner = model
-    while not isinstance(inner, (MDM, ClassifierFreeSampleModel)) and hasattr(inner, "model"):
+    while isinstance(inner, _WrappedModel):
         inner = inner.model
     if isinstance(inner, ClassifierFreeSampleModel):
+        if not isinstance(inner.model, MDM):
+            raise TypeError("ClassifierFreeSampleModel must wrap a b200mdm MDM (got %r)" % type(inner.model))
         return inner.model.engine(), True
     if isinstance(inner, MDM):
         return inner.engine(), False
-    raise TypeError("b200mdm diffusion objects drive b200mdm models only (got %r)" % type(model))
+    raise TypeError("b200mdm diffusion objects drive b200mdm.MDM or b200mdm.ClassifierFreeSampleModel only (got %r); "
+                    "wrap the model with the classes of this package" % type(model))

@@ -5,9 +5,12 @@ into contiguous per-rank slices; the ONLY collective of the path is one broadcas
 (the reference encodes the prompts once per loop, diffusion/gaussian_diffusion.py:633-635), plus an optional gather
 of the finished motions.  Nothing crosses GPUs inside the loop.
 
-Determinism: with ``noise_mode="global"`` every rank draws the SAME global noise stream (same generator seed) and
-keeps its slice, so the G-GPU result is bitwise identical to the 1-GPU result for that seed.
-``noise_mode="per_rank"`` draws only the local slice (rank-dependent stream; cheaper for 1000-step loops).
+Determinism: ``noise_mode="philox"`` (default) uses the engine's counter-based noise stream keyed by (seed, step,
+GLOBAL sample index) -- each rank generates exactly its own samples' noise inside the step graph (no tape, no redundant
+draws) and the G-GPU result is bitwise identical to the 1-GPU result for that seed.  ``noise_mode="global"`` gets the same
+property from torch's generator by drawing the global batch on every rank and keeping a slice (G-fold redundant RNG, done
+step by step so that only one step of global noise is alive at a time); ``noise_mode="per_rank"`` lets each rank draw
+its slice from its own torch stream (rank-dependent results).
 
 One process per GPU, ``torch.distributed`` (backend nccl on GPUs; the same code runs on gloo/CPU in the tests).
 """
@@ -58,7 +61,7 @@ def shard_model_kwargs(model_kwargs, lo, hi):
     return {**model_kwargs, "y": out}
 
 
-def sample_sharded(sample_fn, model, shape, model_kwargs, *, n_steps, noise_mode="global", seed=None, device=None,
+def sample_sharded(sample_fn, model, shape, model_kwargs, *, n_steps, noise_mode="philox", seed=None, device=None,
                    gather=True, group=None, **kwargs):
     """Run `sample_fn` (e.g. ``diffusion.p_sample_loop``) on this rank's slice of the batch.
 
@@ -69,6 +72,10 @@ def sample_sharded(sample_fn, model, shape, model_kwargs, *, n_steps, noise_mode
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     B = int(shape[0])
+    if B < world:
+        # a rank with an empty shard would skip the loop but still has to meet the others in the collectives; the
+        # reference never samples fewer motions than it has GPUs -- refuse up front instead of hanging in all_gather
+        raise ValueError("global batch %d is smaller than the number of ranks %d" % (B, world))
     lo, hi = shard_range(B, rank, world)
     y = model_kwargs["y"]
     if torch.is_tensor(y.get("text_embed")) or isinstance(y.get("text_embed"), tuple):
@@ -79,22 +86,28 @@ def sample_sharded(sample_fn, model, shape, model_kwargs, *, n_steps, noise_mode
         te = y.get("text_embed")
         te = te[0] if isinstance(te, tuple) else te
         device = te.device if torch.is_tensor(te) else torch.device("cpu")
-    gen = None
-    if seed is not None:
-        gen = torch.Generator(device=device)
-        gen.manual_seed(seed if noise_mode == "global" else seed + 7919 * rank)
-    if noise_mode == "global":
-        # identical stream on every rank, in the reference's draw order: x_T, then one eps per step
-        x_T = torch.randn(tuple(shape), device=device, generator=gen)[lo:hi].contiguous()
-        tape = torch.empty((n_steps,) + local_shape, device=device)
-        for k in range(n_steps):
-            tape[k] = torch.randn(tuple(shape), device=device, generator=gen)[lo:hi]
-    elif noise_mode == "per_rank":
-        x_T = torch.randn(local_shape, device=device, generator=gen)
-        tape = torch.randn((n_steps,) + local_shape, device=device, generator=gen)
+    if noise_mode == "philox":
+        # engine stream: x_T and every eps are functions of (seed, step, global sample index) -- nothing is drawn here
+        local = sample_fn(model, local_shape, model_kwargs=local_kwargs, noise_seed=0 if seed is None else seed,
+                          sample_index_base=lo, **kwargs)
     else:
-        raise ValueError("noise_mode must be 'global' or 'per_rank'")
-    local = sample_fn(model, local_shape, noise=x_T, model_kwargs=local_kwargs, noise_tape=tape, **kwargs)
+        gen = None
+        if seed is not None:
+            gen = torch.Generator(device=device)
+            gen.manual_seed(seed if noise_mode == "global" else seed + 7919 * rank)
+        if noise_mode == "global":
+            # identical stream on every rank, in the reference's draw order: x_T, then one eps per step; one global
+            # step is alive at a time (the local tape is still O(n_steps): use "philox" for 1000-step loops)
+            x_T = torch.randn(tuple(shape), device=device, generator=gen)[lo:hi].contiguous()
+            tape = torch.empty((n_steps,) + local_shape, device=device)
+            for k in range(n_steps):
+                tape[k] = torch.randn(tuple(shape), device=device, generator=gen)[lo:hi]
+        elif noise_mode == "per_rank":
+            x_T = torch.randn(local_shape, device=device, generator=gen)
+            tape = torch.randn((n_steps,) + local_shape, device=device, generator=gen)
+        else:
+            raise ValueError("noise_mode must be 'philox', 'global' or 'per_rank'")
+        local = sample_fn(model, local_shape, noise=x_T, model_kwargs=local_kwargs, noise_tape=tape, **kwargs)
     if not gather or world == 1:
         return local
     # all_gather wants equal shapes: pad every shard to the largest one, trim after the exchange

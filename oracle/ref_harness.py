@@ -24,7 +24,21 @@ from types import SimpleNamespace
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("MDM_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _reference_root():
+    """MDM_REFERENCE_ROOT if set; else the read-only reference tree of the build container; else `oracle/_ref/`, the
+    byte-for-byte copy of the 15 hot-path files made by oracle/build_ref.py (what travels to the GPU box)."""
+    env = os.environ.get("MDM_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/diffusion"):
+        return "/root/reference"
+    return os.path.join(_HERE, "_ref")
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 def available():
