@@ -6,7 +6,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libb200mdm.so")
+LIB_PATH = os.environ.get("B200MDM_LIB") or os.path.join(HERE, "lib", "libb200mdm.so")   # (override: A/B builds of the same ABI)
 
 OK, EINVAL, ECUDA, ESTATE, ENOTIMPL = 0, -1, -2, -3, -4
 ARCH = {"trans_enc": 0, "trans_dec": 1}

@@ -12,11 +12,15 @@
 // Epilogue, thread = row, warps (q = lane quarter, part = 128-column half of the CTA's 256 columns):
 //   pass 1    v = acc + bias + residual (TMA-loaded slabs); per-row partial sum / sum of squares; v -> TMEM (in place)
 //   exchange  partials of the two parts meet in shared memory (named barrier); the part-0 warp pushes the CTA's partial
-//             into the PEER CTA's shared memory (st.shared::cluster) and signals the peer's mbarrier; both CTAs now own
-//             the statistics of the complete 512-wide rows
+//             into the PEER CTA's shared memory with st.async (data + mbarrier complete_tx in one message, no release
+//             fence: round 1's `mbarrier.arrive.release.cluster` showed up as stall_membar 0.5 per issue); both CTAs now
+//             own the statistics of the complete 512-wide rows
 //   pass 2    y = (v - mean) rstd gamma + beta -> [hi | lo] fp16 slab -> TMA store
 // History (profiles/): an fp32 stream + separate fp16 copy cost 6 B/element of stores and 41.6 / 49.2 us per launch;
-// TMA slabs beat direct 256-bit loads/stores (43.8 / 51.8 us vs 52.0 / 59.7 us).
+// TMA slabs beat direct 256-bit loads/stores (43.8 / 51.8 us vs 52.0 / 59.7 us).  Round 2: keeping v in 128 registers
+// (one TMEM read instead of read + write-back + read; 12 warps with setmaxnreg) did not shorten the tile loop -- the
+// kernel is bound by L2 -> shared-memory bytes (operands + residual, ~49 B/clk/SM), not by tcgen05.ld -- and cost 5 % of
+// the sampling loop (A/B on one box: 81.7 vs 77.9 ms), so it was not kept; st.async alone gave 78.1 -> 76.9 ms.
 #pragma once
 #include "epilogues.cuh"
 #include "gemm.cuh"
@@ -108,7 +112,7 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], GLN_EPI_WARPS);
     }
-    for (int s = 0; s < 8; ++s) mbar_init(&xbar[s], 32);   // the 32 lanes of the peer's part-0 warp of that quarter
+    for (int s = 0; s < 8; ++s) mbar_init(&xbar[s], 1);    // one expect_tx arrival; the peer's 32 lanes deliver 256 bytes with st.async
     for (int s = 0; s < GLN_EPI_WARPS * 2; ++s) mbar_init(&rbar[s], 1);
     fence_barrier_init();
   }
@@ -199,6 +203,7 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
         load_resid(rseq, 0);
         load_resid(rseq + 1, 1);
       }
+      if (part == 0 && lane == 0) mbar_expect_tx(&xbar[(it & 1) * 4 + q], 256);
       long long* tr = (g_gemm2_trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && it >= 1 && it < 3) ? g_gemm2_trace + (it - 1) * 16 : nullptr;
       int tri = 0;
       if (tr) tr[tri++] = clock64();
@@ -245,9 +250,8 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
       named_bar_sync(1 + q, 64);
       if (part == 0) {
         const float2 a = st_part0[sidx], b = st_part1[sidx];
-        const uint32_t peer_slot = mapa_shared(smem_u32(&st_remote[sidx]), rank ^ 1);
-        st_shared_cluster_f32x2(peer_slot, a.x + b.x, a.y + b.y);
-        mbar_arrive_remote(mapa_shared(smem_u32(&xbar[as * 4 + q]), rank ^ 1));   // release.cluster, one per lane
+        st_async_f32x2(mapa_shared(smem_u32(&st_remote[sidx]), rank ^ 1), a.x + b.x, a.y + b.y,
+                       mapa_shared(smem_u32(&xbar[as * 4 + q]), rank ^ 1));
       }
       mbar_wait_cluster(&xbar[as * 4 + q], aphase);   // the peer's 32 lanes have delivered their partials
       const float2 p0 = st_part0[sidx], p1 = st_part1[sidx], pr = st_remote[sidx];

@@ -385,6 +385,13 @@ __device__ __forceinline__ void umma_f16_ts_2cta(uint32_t tmem_d, uint32_t tmem_
 __device__ __forceinline__ void st_shared_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// 8 bytes into the shared memory of a peer CTA + complete_tx(8) on an mbarrier of that CTA, as ONE asynchronous message:
+// the receiver sees the data once its barrier phase completes; the sender needs no fence.
+__device__ __forceinline__ void st_async_f32x2(uint32_t remote_addr, float a, float b, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(remote_addr), "f"(a), "f"(b), "r"(remote_bar)
+               : "memory");
+}
 // generic-proxy writes (local or remote shared memory) -> visible to the async proxy (TMA, tensor-core operand reads)
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 }  // namespace b200

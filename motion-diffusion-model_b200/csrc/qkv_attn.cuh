@@ -20,18 +20,29 @@
 //   4. softmax     thread = query row, two warps per row (128 keys each, max / sum exchanged through shared memory);
 //        P -> TMEM as fp16
 //   5. O = P V     A = P from TMEM, B = V (MN-major), 16 UMMAs;  6. O / rowsum -> fp16 -> swizzled slabs -> TMA store
-// TMEM (512 columns per CTA): [0,256) Q|K accumulator, later O in [0,128) and P in [128,256); [256,384) V accumulator;
-// [256,512) S.  The phases of one item are serial (the next item's operand loads run ahead through the ring).
+// TMEM (512 columns per CTA): [0,256) Q|K accumulator, then S (it may be overwritten as soon as Q and K have been read,
+// while V is still being converted), then P as fp16 over the first half of each warp's own S columns ([0,64) and
+// [128,192)); [256,384) V accumulator; O in [384,512) -- outside the projection accumulator, so the next item's projection
+// MMAs are issued right behind this item's P V and run under its output epilogue.
+// What bounds the CUDA-core side (measured, profiles/r02_a_trace_qkv_attn_v1.txt): tcgen05.ld moves 16 B/clk per lane
+// quarter, i.e. a [128 x N] fp32 accumulator costs 8 N cycles per read -- 3072 for the projection, 2048 for S, 1024 for
+// O.  Every TMEM value is therefore read exactly once (S is held in 128 registers between the max and the exp pass).
 #pragma once
 #include <cuda_fp16.h>
 
 #include "attention_tc.cuh"   // tmem_st_32x16
+#include "gemm2.cuh"          // g_gemm2_trace (debug stamps)
 #include "epilogues.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
 
-constexpr int QA_THREADS = 320;              // warp 0 TMA, warp 1 MMA / TMEM, warps 2-9 epilogue + softmax
+constexpr int QA_THREADS = 384;              // warpgroup 0: warp 0 TMA, warp 1 MMA / TMEM, warps 2-3 idle; warpgroups 1-2: epilogue
+// Registers: 12 warps = 3 per SM sub-partition = 168 registers per thread at launch.  The epilogue warps hold a whole
+// 128-key row of S (and the LayerNorm-style single-read epilogues 128 accumulator values) in registers, so warpgroup 0
+// hands its share back (setmaxnreg.dec) and the epilogue warpgroups grow: CTRL + 2 x EPI <= 512 per lane.  The two setmaxnreg
+// must sit INSIDE the role branches: after a join ptxas compiles everything for the smaller count.
+constexpr int QA_REGS_CTRL = 88, QA_REGS_EPI = 208;   // 88 + 2 x 208 = 504 = 3 x 168: the pool is what the CTA got at launch
 constexpr int QA_STAGES = 3;
 constexpr int QA_STAGE_BYTES = 16384 + 16384 + 8192;   // A [128 x 64] | W (q or k) [128 x 64] | W (v half) [64 x 64]
 constexpr int QA_TILE = 32768;               // [128 x 128] fp16
@@ -66,9 +77,9 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
   uint64_t* full_bar = bars;                 // [3]  leader's copy is live (expect_tx of both CTAs' bytes)
   uint64_t* empty_bar = bars + 3;            // [3]  multicast commit
   uint64_t* proj_done = bars + 6;            //      multicast commit: accumulator complete
-  uint64_t* qkv_ready = bars + 7;            //      leader: 16 warp arrivals (both CTAs): Q, K, V are in shared memory
+  uint64_t* qkv_ready = bars + 7;            //      leader: 16 warp arrivals (both CTAs): Q and K are in shared memory
   uint64_t* s_done = bars + 8;               //      multicast commit: S complete
-  uint64_t* p_ready = bars + 9;              //      leader: 16 warp arrivals: P is in TMEM
+  uint64_t* p_ready = bars + 9;              //      leader: 16 warp arrivals: P is in TMEM, V (incl. the peer's half) in shared memory
   uint64_t* o_done = bars + 10;              //      multicast commit: O complete
   uint64_t* tmem_free = bars + 11;           //      leader: 16 warp arrivals: O has been read
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
@@ -108,79 +119,11 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
 
-  if (warp == 0) {
-    // ---------------------------------------------------------------- TMA producer (both CTAs)
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = cluster_id; item < num_items; item += num_clusters) {
-        const int smp = item >> 2, h = item & 3;
-        const int wrow = (leader ? 0 : 512) + h * 128;          // Wq_h rows (CTA 0) / Wk_h rows (CTA 1)
-        const int vrow = 1024 + h * 128 + 64 * static_cast<int>(rank);
-        for (int kb = 0; kb < 8; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = ring + stage * QA_STAGE_BYTES;
-          const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * QA_STAGE_BYTES);
-          tma_load_3d_2cta(sa, &map_h, leader_full, kb * 64, 128 * static_cast<int>(rank), smp);
-          tma_load_2d_2cta(sa + 16384, &map_w128, leader_full, kb * 64, wrow);
-          tma_load_2d_2cta(sa + 32768, &map_w64, leader_full, kb * 64, vrow);
-          if (++stage == QA_STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer (leader only)
-    if (leader && elect_one()) {
-      constexpr uint32_t idesc_qk = umma_idesc_f16(256, 256);
-      constexpr uint32_t idesc_v = umma_idesc_f16(256, 128);
-      constexpr uint32_t idesc_s = umma_idesc_f16(256, 256);
-      constexpr uint32_t idesc_o = umma_idesc_f16(256, 128, 0, 1);   // B (= V) is MN-major
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
-        const uint32_t par = it & 1;
-        if (it > 0) mbar_wait_cluster(tmem_free, par ^ 1);      // O of the previous item has been read in both CTAs
-        tc_fence_after();
-        for (int kb = 0; kb < 8; ++kb) {
-          mbar_wait_cluster(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(ring + stage * QA_STAGE_BYTES);
-          const uint64_t da = umma_desc_k_sw128(sa), db1 = umma_desc_k_sw128(sa + 16384), db2 = umma_desc_k_sw128(sa + 32768);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_f16_ss_2cta(tmem_base, da + 2 * k, db1 + 2 * k, idesc_qk, (kb | k) != 0);
-            umma_f16_ss_2cta(tmem_base + 256, da + 2 * k, db2 + 2 * k, idesc_v, (kb | k) != 0);
-          }
-          umma_commit_2cta_mc(&empty_bar[stage], 0b11);
-          if (++stage == QA_STAGES) { stage = 0; phase ^= 1; }
-        }
-        umma_commit_2cta_mc(proj_done, 0b11);
-        // S = Q K^T
-        mbar_wait_cluster(qkv_ready, par);
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
-          umma_f16_ss_2cta(tmem_base + 256, umma_desc_k_sw128(smem_u32(sQ) + off), umma_desc_k_sw128(smem_u32(sK) + off),
-                           idesc_s, ks != 0);
-        }
-        umma_commit_2cta_mc(s_done, 0b11);
-        // O = P V
-        mbar_wait_cluster(p_ready, par);
-        tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < 16; ++kk)
-          umma_f16_ts_2cta(tmem_base, tmem_base + 128 + kk * 8, umma_desc_mn_sw128(smem_u32(sV) + kk * 2048, 0, 1024),
-                           idesc_o, kk != 0);
-        umma_commit_2cta_mc(o_done, 0b11);
-      }
-    }
-  } else {
-    // ---------------------------------------------------------------- epilogue / softmax warps (2..9), both CTAs
+  if (warp >= 4) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(QA_REGS_EPI));
+    // ---------------------------------------------------------------- epilogue / softmax warps (4..11), both CTAs
     const int q = warp & 3;                    // TMEM lane quarter
-    const int part = (warp - 2) >> 2;          // 0: Q columns + dh [0,64) of V + keys [0,128); 1: K + dh [64,128) + keys [128,256)
+    const int part = (warp - 4) >> 2;          // 0: Q columns + dh [0,64) of V + keys [0,128); 1: K + dh [64,128) + keys [128,256)
     const int row = 32 * q + lane;             // token row inside this CTA's tile
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(32 * q) << 16);
     const uint32_t qkv_ready_leader = mapa_shared(smem_u32(qkv_ready), 0);
@@ -201,8 +144,11 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
       const uint32_t par = it & 1;
       const int smp = item >> 2, h = item & 3;
       const int kvl = min(kvlen[smp], S);
+      long long* tr = (g_gemm2_trace != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0 && it >= 1 && it < 3) ? g_gemm2_trace + (it - 1) * 16 : nullptr;
+      if (tr) tr[0] = clock64();
       mbar_wait(proj_done, par);
       tc_fence_after();
+      if (tr) tr[1] = clock64();
       // the previous item's output slabs live in the Q tile: their TMA stores must have finished reading
       if (lane == 0) bulk_wait_group_read<0>();
       named_bar_sync(1 + q, 64);
@@ -251,50 +197,55 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
         tmem_ld_wait();
         tmem_ld_32x32(tv, ra);
         store_qk(rb, 3);
+        // Q / K are complete: let S = Q K^T start while V is still being written.  Only LOCAL stores precede this
+        // release, so it does not have to wait for distributed-shared-memory traffic.
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(qkv_ready_leader);   // release.cluster
+        if (tr) tr[2] = clock64();
         tmem_ld_wait();
         tmem_ld_32x32(tv + 32, rb);
         store_v(ra, 0);
         tmem_ld_wait();
         store_v(rb, 1);
+        // (the V half that went to the peer is published together with P, below)
       }
-      fence_proxy_async_all();      // operand tiles (own and the peer's V half) -> visible to the tensor cores
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(qkv_ready_leader);   // release.cluster
-      // ---- softmax over this warp's 128 keys of S (columns 256 + 128 part ...), row max / sum shared with the partner warp
+      if (tr) tr[3] = clock64();
+      // ---- softmax over this warp's 128 keys of S (columns 128 part ...): ONE read of S into 128 registers, row
+      // max / sum shared with the partner warp through shared memory
       mbar_wait(s_done, par);
       tc_fence_after();
-      const uint32_t tS = trow + 256 + 128 * part;
+      if (tr) tr[4] = clock64();
       const int key0 = 128 * part;
-      float mx = -INFINITY;
+      float sum = 0.f;
       {
-        uint32_t ra[32], rb[32];
+        const uint32_t tS = trow + 128 * part;       // this warp's 128 keys of S
+        const uint32_t tP = tS;                      // P (fp16 pairs, 64 columns) over the S columns already held in registers
+        // 32-key chunks of this warp that contain at least one valid key (warp-uniform): the others are neither read
+        // nor exponentiated, and the P V MMAs stop at ceil(kvl / 16) key steps
+        const int nch = min(4, max(part == 0 ? 1 : 0, (kvl - key0 + 31) >> 5));   // (part 0 always writes P chunk 0)
+        uint32_t r0[32], r1[32], r2[32], r3[32];
+        if (nch > 0) tmem_ld_32x32(tS, r0);
+        if (nch > 1) tmem_ld_32x32(tS + 32, r1);
+        if (nch > 2) tmem_ld_32x32(tS + 64, r2);
+        if (nch > 3) tmem_ld_32x32(tS + 96, r3);
+        tmem_ld_wait();
+        float mx = -INFINITY;
         auto max32 = [&](const uint32_t (&r)[32], int c) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (key0 + 32 * c + j < kvl) mx = fmaxf(mx, __uint_as_float(r[j]));
         };
-        tmem_ld_32x32(tS, ra);
-        tmem_ld_wait();
-        tmem_ld_32x32(tS + 32, rb);
-        max32(ra, 0);
-        tmem_ld_wait();
-        tmem_ld_32x32(tS + 64, ra);
-        max32(rb, 1);
-        tmem_ld_wait();
-        tmem_ld_32x32(tS + 96, rb);
-        max32(ra, 2);
-        tmem_ld_wait();
-        max32(rb, 3);
-      }
-      xmax[part * 128 + row] = mx;
-      named_bar_sync(1 + q, 64);
-      mx = fmaxf(xmax[row], xmax[128 + row]);
-      const float off = (mx == -INFINITY) ? 0.f : mx * scale_log2;
-      float sum = 0.f;
-      {
-        const uint32_t tP = trow + 128 + 64 * part;
-        uint32_t ra[32], rb[32];
+        if (nch > 0) max32(r0, 0);
+        if (nch > 1) max32(r1, 1);
+        if (nch > 2) max32(r2, 2);
+        if (nch > 3) max32(r3, 3);
+        if (tr) tr[5] = clock64();
+        xmax[part * 128 + row] = mx;
+        named_bar_sync(1 + q, 64);
+        mx = fmaxf(xmax[row], xmax[128 + row]);
+        const float off = (mx == -INFINITY) ? 0.f : mx * scale_log2;
         auto softmax32 = [&](const uint32_t (&r)[32], int c) {
           uint32_t pk[16];
 #pragma unroll
@@ -308,32 +259,27 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
           }
           tmem_st_32x16(tP + 16 * c, pk);
         };
-        tmem_ld_32x32(tS, ra);
-        tmem_ld_wait();
-        tmem_ld_32x32(tS + 32, rb);
-        softmax32(ra, 0);
-        tmem_ld_wait();
-        tmem_ld_32x32(tS + 64, ra);
-        softmax32(rb, 1);
-        tmem_ld_wait();
-        tmem_ld_32x32(tS + 96, rb);
-        softmax32(ra, 2);
-        tmem_ld_wait();
-        softmax32(rb, 3);
+        if (nch > 0) softmax32(r0, 0);
+        if (nch > 1) softmax32(r1, 1);
+        if (nch > 2) softmax32(r2, 2);
+        if (nch > 3) softmax32(r3, 3);
       }
       xsum[part * 128 + row] = sum;
       tmem_st_wait();
+      fence_proxy_async_all();      // this warp's V rows (local or in the peer's shared memory) -> visible to the tensor cores
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(p_ready_leader);
+      if (lane == 0) mbar_arrive_remote(p_ready_leader);   // release.cluster
+      if (tr) tr[6] = clock64();
       // ---- O / rowsum -> fp16 -> slab -> TMA store (this warp: rows [32q, +32), dh [64 part, +64))
       mbar_wait(o_done, par);
       tc_fence_after();
+      if (tr) tr[7] = clock64();
       named_bar_sync(1 + q, 64);
       const float tot = xsum[row] + xsum[128 + row];
       const float inv = tot > 0.f ? 1.f / tot : 0.f;
       {
-        const uint32_t tO = trow + 64 * part;
+        const uint32_t tO = trow + 384 + 64 * part;
         uint32_t ra[32], rb[32];
         tmem_ld_32x32(tO, ra);
         tmem_ld_32x32(tO + 32, rb);
@@ -364,9 +310,91 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
         }
       }
       __syncwarp();
+      if (tr) tr[8] = clock64();
     }
     if (lane == 0) bulk_wait_group<0>();
     __syncwarp();
+  
+  } else {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(QA_REGS_CTRL));
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer (both CTAs)
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        const int smp = item >> 2, h = item & 3;
+        const int wrow = (leader ? 0 : 512) + h * 128;          // Wq_h rows (CTA 0) / Wk_h rows (CTA 1)
+        const int vrow = 1024 + h * 128 + 64 * static_cast<int>(rank);
+        for (int kb = 0; kb < 8; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = ring + stage * QA_STAGE_BYTES;
+          const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * QA_STAGE_BYTES);
+          tma_load_3d_2cta(sa, &map_h, leader_full, kb * 64, 128 * static_cast<int>(rank), smp);
+          tma_load_2d_2cta(sa + 16384, &map_w128, leader_full, kb * 64, wrow);
+          tma_load_2d_2cta(sa + 32768, &map_w64, leader_full, kb * 64, vrow);
+          if (++stage == QA_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer (leader only)
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc_qk = umma_idesc_f16(256, 256);
+      constexpr uint32_t idesc_v = umma_idesc_f16(256, 128);
+      constexpr uint32_t idesc_s = umma_idesc_f16(256, 256);
+      constexpr uint32_t idesc_o = umma_idesc_f16(256, 128, 0, 1);   // B (= V) is MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
+        const uint32_t par = it & 1;
+        const int nk16 = max(1, (min(kvlen[item >> 2], S) + 15) >> 4);   // 16-key steps of P V that hold a valid key
+        long long* tr = (g_gemm2_trace != nullptr && cluster_id == 0 && it >= 1 && it < 3) ? g_gemm2_trace + 32 + (it - 1) * 8 : nullptr;
+        if (tr) tr[0] = clock64();
+        // projection: [0,384) was last read by the previous item's projection epilogue (Q|K, V accumulators: the previous
+        // qkv_ready / p_ready were waited for) and by the previous P V MMA (P in [128,256): MMAs execute in issue order)
+        for (int kb = 0; kb < 8; ++kb) {
+          mbar_wait_cluster(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + stage * QA_STAGE_BYTES);
+          const uint64_t da = umma_desc_k_sw128(sa), db1 = umma_desc_k_sw128(sa + 16384), db2 = umma_desc_k_sw128(sa + 32768);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_f16_ss_2cta(tmem_base, da + 2 * k, db1 + 2 * k, idesc_qk, (kb | k) != 0);
+            umma_f16_ss_2cta(tmem_base + 256, da + 2 * k, db2 + 2 * k, idesc_v, (kb | k) != 0);
+          }
+          umma_commit_2cta_mc(&empty_bar[stage], 0b11);
+          if (++stage == QA_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta_mc(proj_done, 0b11);
+        if (tr) tr[1] = clock64();
+        // S = Q K^T over the (read) Q|K accumulator columns [0,256)
+        mbar_wait_cluster(qkv_ready, par);
+        tc_fence_after();
+        if (tr) tr[2] = clock64();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
+          umma_f16_ss_2cta(tmem_base, umma_desc_k_sw128(smem_u32(sQ) + off), umma_desc_k_sw128(smem_u32(sK) + off),
+                           idesc_s, ks != 0);
+        }
+        umma_commit_2cta_mc(s_done, 0b11);
+        // O = P V into [384,512): the previous item's O has been read by the output epilogues of both CTAs
+        mbar_wait_cluster(p_ready, par);
+        if (it > 0) mbar_wait_cluster(tmem_free, par ^ 1);
+        tc_fence_after();
+        if (tr) tr[3] = clock64();
+#pragma unroll 4
+        for (int kk = 0; kk < nk16; ++kk)
+          umma_f16_ts_2cta(tmem_base + 384, tmem_base + (kk >> 3) * 128 + (kk & 7) * 8,
+                           umma_desc_mn_sw128(smem_u32(sV) + kk * 2048, 0, 1024), idesc_o, kk != 0);
+        umma_commit_2cta_mc(o_done, 0b11);
+        if (tr) tr[4] = clock64();
+      }
+    }
+  }
   }
 
   tc_fence_before();

@@ -17,11 +17,14 @@ for K in (512, 1024):
     buf.zero_(); lib.b200mdm_debug_trace(buf.data_ptr()); call(); torch.cuda.synchronize(); lib.b200mdm_debug_trace(None)
     t = buf.cpu().tolist()
     for it in range(2):
-        r = t[it*16:it*16+11]
-        print("K=%d tile %d: acc_full wait %d | pass1 chunks %s | exchange %d | pass2 chunks %s" % (K, it + 1, r[1]-r[0],
-              [r[i+1]-r[i] for i in range(1, 5)], r[6]-r[5], [r[i+1]-r[i] for i in range(6, 10)]))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10): call()
-    e1.record(); torch.cuda.synchronize()
-    print("K=%d: %.1f us per launch" % (K, e0.elapsed_time(e1) * 100))
+        r = t[it*16:it*16+5]
+        print("K=%d tile %d: acc_full wait %d | pass 1 (single TMEM read, v in registers) %d | statistics exchange %d | pass 2 + stores %d"
+              % (K, it + 1, r[1]-r[0], r[2]-r[1], r[3]-r[2], r[4]-r[3]))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); call(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    print("K=%d: %.1f us per launch (L2 flushed), %.0f TFLOP/s" % (K, sum(ts) / len(ts), 2.0 * M * 512 * K / (sum(ts) / len(ts)) / 1e6))
