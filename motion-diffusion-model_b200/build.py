@@ -44,8 +44,21 @@ def _stale():
     return any(os.path.getmtime(p) > t for p in deps if os.path.exists(p))
 
 
-def build(force=False, verbose=False):
-    """Compile csrc/*.cu into lib/libb200mdm.so.  Returns the library path."""
+def build(force=False, verbose=False, trace=None):
+    """Compile csrc/*.cu into lib/libb200mdm.so.  Returns the library path.
+    trace (or B200MDM_TRACE=1): the instrumented variant lib/libb200mdm_trace.so (-DB200_TRACE: clock64 phase stamps for
+    tools/trace_*.py; run them with B200MDM_LIB pointing at it)."""
+    if trace is None:
+        trace = os.environ.get("B200MDM_TRACE", "0") == "1"
+    if trace:
+        path = os.path.join(LIB_DIR, "libb200mdm_trace.so")
+        os.makedirs(LIB_DIR, exist_ok=True)
+        proc = subprocess.run([_nvcc()] + NVCC_FLAGS + ["-DB200_TRACE", "-o", path] + sources(), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True)
+        if proc.returncode != 0:
+            sys.stderr.write(proc.stdout)
+            raise RuntimeError("nvcc failed (exit %d)" % proc.returncode)
+        return path
     if not force and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)

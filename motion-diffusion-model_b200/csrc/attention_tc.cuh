@@ -137,7 +137,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   } else {
     // ------------------------------------------------------------------ softmax + output warps
     const int q = warp & 3;             // TMEM lane quarter
-    long long* tr = (g_gemm2_trace != nullptr && blockIdx.x == 1 && blockIdx.y == 37 && blockIdx.z == 0 && warp == 2 && lane == 0) ? g_gemm2_trace : nullptr;
+    long long* tr = B200_TRACE_PTR(blockIdx.x == 1 && blockIdx.y == 37 && blockIdx.z == 0 && warp == 2 && lane == 0, g_gemm2_trace);
     if (tr) tr[0] = clock64();
     const int kvl = min(kvlen[smp], S);
     const uint32_t tS = tmem_base + (static_cast<uint32_t>(q * 32) << 16);

@@ -19,8 +19,16 @@
 
 namespace b200 {
 
-// debug: clock64 stamps of cluster 0 (MMA issuer: 4 per tile; first epilogue warp: 3 per tile); null in production
+// debug: clock64 stamps of cluster 0 (MMA issuer / first epilogue warp).  Compiled in only with -DB200_TRACE (the
+// tools/trace_*.py build: B200MDM_TRACE=1 python -m b200mdm.build -> lib/libb200mdm_trace.so): in a production build the
+// pointer test was a dependent global load at the head of every tile / item of every hot kernel (3.8 % + 2.9 % of the
+// LayerNorm-GEMM's stall samples, profiles/r02_e_ncu_gemm_resid_ln_cluster.txt).
 __device__ long long* g_gemm2_trace = nullptr;
+#ifdef B200_TRACE
+#define B200_TRACE_PTR(cond, ptr) ((b200::g_gemm2_trace != nullptr && (cond)) ? (ptr) : static_cast<long long*>(nullptr))
+#else
+#define B200_TRACE_PTR(cond, ptr) (static_cast<long long*>(nullptr))
+#endif
 
 constexpr int GEMM2_BLOCK_N = 256;   // per pair: 256 x 256 output tile; per CTA: 128 rows x 256 columns of accumulator
 constexpr int GEMM2_TILE_M = 256;
@@ -131,7 +139,7 @@ gemm2_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        long long* tr = (g_gemm2_trace != nullptr && cluster_id == 0 && it < 8) ? g_gemm2_trace + it * 8 : nullptr;
+        long long* tr = B200_TRACE_PTR(cluster_id == 0 && it < 8, g_gemm2_trace + it * 8);
         if (tr) tr[0] = clock64();
         mbar_wait_cluster(&acc_empty[as], aphase ^ 1);
         tc_fence_after();
@@ -176,7 +184,7 @@ gemm2_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint32_t aphase = (it >> 1) & 1;
       const int row0 = m_blk * GEMM2_TILE_M + static_cast<int>(rank) * 128 + q * 32;
       const uint32_t taddr = tmem_base + as * ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
-      long long* tr = (g_gemm2_trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && it < 8) ? g_gemm2_trace + it * 8 : nullptr;
+      long long* tr = B200_TRACE_PTR(blockIdx.x == 0 && warp == 2 && lane == 0 && it < 8, g_gemm2_trace + it * 8);
       if (tr) tr[4] = clock64();
       if (tr) { mbar_wait(&acc_full[as], aphase); tr[5] = clock64(); }
       ctx.trace = (tr && it >= 2 && it < 6) ? g_gemm2_trace + 64 + (it - 2) * 16 : nullptr;

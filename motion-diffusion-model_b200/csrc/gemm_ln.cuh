@@ -204,7 +204,7 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
         load_resid(rseq + 1, 1);
       }
       if (part == 0 && lane == 0) mbar_expect_tx(&xbar[(it & 1) * 4 + q], 256);
-      long long* tr = (g_gemm2_trace != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0 && it >= 1 && it < 3) ? g_gemm2_trace + (it - 1) * 16 : nullptr;
+      long long* tr = B200_TRACE_PTR(blockIdx.x == 0 && warp == 2 && lane == 0 && it >= 1 && it < 3, g_gemm2_trace + (it - 1) * 16);
       int tri = 0;
       if (tr) tr[tri++] = clock64();
       mbar_wait(&acc_full[as], aphase);

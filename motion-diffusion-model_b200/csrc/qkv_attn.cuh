@@ -21,8 +21,7 @@
 //        P -> TMEM as fp16
 //   5. O = P V     A = P from TMEM, B = V (MN-major), 16 UMMAs;  6. O / rowsum -> fp16 -> swizzled slabs -> TMA store
 // TMEM (512 columns per CTA): [0,256) Q|K accumulator, then S (it may be overwritten as soon as Q and K have been read,
-// while V is still being converted), then P as fp16 over the first half of each warp's own S columns ([0,64) and
-// [128,192)); [256,384) V accumulator; O in [384,512) -- outside the projection accumulator, so the next item's projection
+// while V is still being converted), then P as fp16 over the first half of each warp's own S columns; [256,384) V accumulator; O in [384,512) -- outside the projection accumulator, so the next item's projection
 // MMAs are issued right behind this item's P V and run under its output epilogue.
 // What bounds the CUDA-core side (measured, profiles/r02_a_trace_qkv_attn_v1.txt): tcgen05.ld moves 16 B/clk per lane
 // quarter, i.e. a [128 x N] fp32 accumulator costs 8 N cycles per read -- 3072 for the projection, 2048 for S, 1024 for
@@ -144,7 +143,7 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
       const uint32_t par = it & 1;
       const int smp = item >> 2, h = item & 3;
       const int kvl = min(kvlen[smp], S);
-      long long* tr = (g_gemm2_trace != nullptr && blockIdx.x == 0 && warp == 4 && lane == 0 && it >= 1 && it < 3) ? g_gemm2_trace + (it - 1) * 16 : nullptr;
+      long long* tr = B200_TRACE_PTR(blockIdx.x == 0 && warp == 4 && lane == 0 && it >= 1 && it < 3, g_gemm2_trace + (it - 1) * 16);
       if (tr) tr[0] = clock64();
       mbar_wait(proj_done, par);
       tc_fence_after();
@@ -212,24 +211,28 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
       }
       tc_fence_before();
       if (tr) tr[3] = clock64();
-      // ---- softmax over this warp's 128 keys of S (columns 128 part ...): ONE read of S into 128 registers, row
-      // max / sum shared with the partner warp through shared memory
+      // ---- softmax: the valid 16-key blocks of S are split evenly between the two warps of a row (at S = 197: 7 + 6 blocks
+      // instead of 8 + 5: the S read and the exponentials are the critical path of the item); ONE read of S into
+      // registers, row max / sum shared with the partner warp through shared memory
       mbar_wait(s_done, par);
       tc_fence_after();
       if (tr) tr[4] = clock64();
-      const int key0 = 128 * part;
+      const int nblk = max(1, (kvl + 15) >> 4);            // 16-key blocks holding a valid key (P V stops there too)
+      const int split_blk = (nblk + 1) >> 1;               // part 0: blocks [0, split), part 1: [split, nblk)
+      const int key0 = part == 0 ? 0 : 16 * split_blk;     // first key (= first S column) of this warp
+      const int nkeys = part == 0 ? 16 * split_blk : 16 * (nblk - split_blk);   // <= 128, multiple of 16
+      const int n32 = nkeys >> 5;
+      const bool tail16 = (nkeys & 16) != 0;
       float sum = 0.f;
       {
-        const uint32_t tS = trow + 128 * part;       // this warp's 128 keys of S
-        const uint32_t tP = tS;                      // P (fp16 pairs, 64 columns) over the S columns already held in registers
-        // 32-key chunks of this warp that contain at least one valid key (warp-uniform): the others are neither read
-        // nor exponentiated, and the P V MMAs stop at ceil(kvl / 16) key steps
-        const int nch = min(4, max(part == 0 ? 1 : 0, (kvl - key0 + 31) >> 5));   // (part 0 always writes P chunk 0)
-        uint32_t r0[32], r1[32], r2[32], r3[32];
-        if (nch > 0) tmem_ld_32x32(tS, r0);
-        if (nch > 1) tmem_ld_32x32(tS + 32, r1);
-        if (nch > 2) tmem_ld_32x32(tS + 64, r2);
-        if (nch > 3) tmem_ld_32x32(tS + 96, r3);
+        const uint32_t tS = trow + key0;
+        const uint32_t tP = trow + key0;               // P (fp16 pairs) over the first half of this warp's own S columns
+        uint32_t r0[32], r1[32], r2[32], r3[32], rt[16];
+        if (n32 > 0) tmem_ld_32x32(tS, r0);
+        if (n32 > 1) tmem_ld_32x32(tS + 32, r1);
+        if (n32 > 2) tmem_ld_32x32(tS + 64, r2);
+        if (n32 > 3) tmem_ld_32x32(tS + 96, r3);
+        if (tail16) tmem_ld_32x16(tS + 32 * n32, rt);
         tmem_ld_wait();
         float mx = -INFINITY;
         auto max32 = [&](const uint32_t (&r)[32], int c) {
@@ -237,10 +240,15 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
           for (int j = 0; j < 32; ++j)
             if (key0 + 32 * c + j < kvl) mx = fmaxf(mx, __uint_as_float(r[j]));
         };
-        if (nch > 0) max32(r0, 0);
-        if (nch > 1) max32(r1, 1);
-        if (nch > 2) max32(r2, 2);
-        if (nch > 3) max32(r3, 3);
+        if (n32 > 0) max32(r0, 0);
+        if (n32 > 1) max32(r1, 1);
+        if (n32 > 2) max32(r2, 2);
+        if (n32 > 3) max32(r3, 3);
+        if (tail16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (key0 + 32 * n32 + j < kvl) mx = fmaxf(mx, __uint_as_float(rt[j]));
+        }
         if (tr) tr[5] = clock64();
         xmax[part * 128 + row] = mx;
         named_bar_sync(1 + q, 64);
@@ -259,10 +267,23 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
           }
           tmem_st_32x16(tP + 16 * c, pk);
         };
-        if (nch > 0) softmax32(r0, 0);
-        if (nch > 1) softmax32(r1, 1);
-        if (nch > 2) softmax32(r2, 2);
-        if (nch > 3) softmax32(r3, 3);
+        if (n32 > 0) softmax32(r0, 0);
+        if (n32 > 1) softmax32(r1, 1);
+        if (n32 > 2) softmax32(r2, 2);
+        if (n32 > 3) softmax32(r3, 3);
+        if (tail16) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const float e0 = ex2(fmaf(__uint_as_float(rt[j]), scale_log2, -off));
+            const float e1 = ex2(fmaf(__uint_as_float(rt[j + 1]), scale_log2, -off));
+            const float p0 = (key0 + 32 * n32 + j < kvl) ? e0 : 0.f;
+            const float p1 = (key0 + 32 * n32 + j + 1 < kvl) ? e1 : 0.f;
+            sum += p0 + p1;
+            pk[j >> 1] = pack_half2(p0, p1);
+          }
+          tmem_st_32x8(tP + 16 * n32, pk);
+        }
       }
       xsum[part * 128 + row] = sum;
       tmem_st_wait();
@@ -351,7 +372,8 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
       for (int item = cluster_id; item < num_items; item += num_clusters, ++it) {
         const uint32_t par = it & 1;
         const int nk16 = max(1, (min(kvlen[item >> 2], S) + 15) >> 4);   // 16-key steps of P V that hold a valid key
-        long long* tr = (g_gemm2_trace != nullptr && cluster_id == 0 && it >= 1 && it < 3) ? g_gemm2_trace + 32 + (it - 1) * 8 : nullptr;
+        const int split_blk = (nk16 + 1) >> 1;                          // P of blocks [0, split) at column 8 kk, the rest at 16 split + 8 (kk - split)
+        long long* tr = B200_TRACE_PTR(cluster_id == 0 && it >= 1 && it < 3, g_gemm2_trace + 32 + (it - 1) * 8);
         if (tr) tr[0] = clock64();
         // projection: [0,384) was last read by the previous item's projection epilogue (Q|K, V accumulators: the previous
         // qkv_ready / p_ready were waited for) and by the previous P V MMA (P in [128,256): MMAs execute in issue order)
@@ -388,7 +410,7 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
         if (tr) tr[3] = clock64();
 #pragma unroll 4
         for (int kk = 0; kk < nk16; ++kk)
-          umma_f16_ts_2cta(tmem_base + 384, tmem_base + (kk >> 3) * 128 + (kk & 7) * 8,
+          umma_f16_ts_2cta(tmem_base + 384, tmem_base + (kk < split_blk ? 8 * kk : 16 * split_blk + 8 * (kk - split_blk)),
                            umma_desc_mn_sw128(smem_u32(sV) + kk * 2048, 0, 1024), idesc_o, kk != 0);
         umma_commit_2cta_mc(o_done, 0b11);
         if (tr) tr[4] = clock64();

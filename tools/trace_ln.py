@@ -1,6 +1,7 @@
 import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("B200MDM_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "motion-diffusion-model_b200", "lib", "libb200mdm_trace.so"))   # -DB200_TRACE build: B200MDM_TRACE=1 python -m b200mdm.build
 from b200mdm import _lib
 lib = _lib.load()
 M = 128 * 197
@@ -17,9 +18,9 @@ for K in (512, 1024):
     buf.zero_(); lib.b200mdm_debug_trace(buf.data_ptr()); call(); torch.cuda.synchronize(); lib.b200mdm_debug_trace(None)
     t = buf.cpu().tolist()
     for it in range(2):
-        r = t[it*16:it*16+5]
-        print("K=%d tile %d: acc_full wait %d | pass 1 (single TMEM read, v in registers) %d | statistics exchange %d | pass 2 + stores %d"
-              % (K, it + 1, r[1]-r[0], r[2]-r[1], r[3]-r[2], r[4]-r[3]))
+        r = t[it*16:it*16+11]
+        print("K=%d tile %d: acc_full wait %d | pass 1 chunks %s | statistics exchange %d | pass 2 chunks %s | tile total %d"
+              % (K, it + 1, r[1]-r[0], [r[i+1]-r[i] for i in range(1, 5)], r[6]-r[5], [r[i+1]-r[i] for i in range(6, 10)], r[10]-r[0]))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     ts = []
     for _ in range(10):
