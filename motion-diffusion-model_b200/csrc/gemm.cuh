@@ -92,27 +92,21 @@ __device__ __forceinline__ void epilogue_tile(EpiCtx& ctx, const typename Epi::P
       Epi::chunk(ctx, ep, raw, row0, col_base + c, (cn < BLOCK_N && col_base + cn < ctx.N) ? col_base + cn : -1);
     if (ctx.trace && ctx.lane == 0) ctx.trace[tr_i++] = clock64();
   };
-  uint32_t raw_a[32], raw_b[32];
-  int c = part * 64;
-  if (c >= BLOCK_N) {
-    done_reading();
-  } else {
-    tmem_ld_32x32(taddr + c, raw_a);
+  // One tcgen05.ld per 64-column block of this warp (two 32-column chunks for the functor): the epilogue of tile i runs
+  // while the MMAs of tile i+1 own the TMEM port, which arbitrates per instruction -- fewer, wider loads wait less.
+  uint32_t raw[64];
 #pragma unroll 1
-    while (true) {
-      const int cn = epi_next_chunk<BLOCK_N>(c);
-      tmem_ld_wait();
-      if (cn < BLOCK_N) tmem_ld_32x32(taddr + cn, raw_b); else done_reading();
-      run(raw_a, c, cn);
-      if (cn >= BLOCK_N) break;
-      const int cnn = epi_next_chunk<BLOCK_N>(cn);
-      tmem_ld_wait();
-      if (cnn < BLOCK_N) tmem_ld_32x32(taddr + cnn, raw_a); else done_reading();
-      run(raw_b, cn, cnn);
-      if (cnn >= BLOCK_N) break;
-      c = cnn;
-    }
+  for (int c = part * 64; c < BLOCK_N; c += 64 * GEMM_EPI_PARTS) {
+    const bool two = c + 32 < BLOCK_N;                       // (BLOCK_N = 96: the last block is a single chunk)
+    const int cnext = c + 64 * GEMM_EPI_PARTS;
+    if (two) tmem_ld_32x64(taddr + c, raw);
+    else tmem_ld_32x32(taddr + c, *reinterpret_cast<uint32_t(*)[32]>(raw));
+    tmem_ld_wait();
+    if (cnext >= BLOCK_N) done_reading();
+    run(*reinterpret_cast<uint32_t(*)[32]>(raw), c, two ? c + 32 : cnext);
+    if (two) run(*reinterpret_cast<uint32_t(*)[32]>(raw + 32), c + 32, cnext);
   }
+  if (part * 64 >= BLOCK_N) done_reading();
   if (live) Epi::tile_end(ctx, ep, row0, col_base, taddr);
 }
 

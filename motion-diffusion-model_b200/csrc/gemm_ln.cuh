@@ -212,35 +212,40 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
       if (tr) tr[tri++] = clock64();
       float sum = 0.f, sumsq = 0.f;
       if (live) {
-        // ---- pass 1
+        // ---- pass 1 (64 accumulator columns per tcgen05.ld / tcgen05.st: the TMEM port arbitrates per instruction while
+        // the next tile's MMAs run, see ptx.cuh)
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t raw[32];
-          tmem_ld_32x32(taddr + 32 * c, raw);
-          mbar_wait(&rb[rseq & 1], (rseq >> 1) & 1);
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t raw[64];
+          tmem_ld_32x64(taddr + 64 * cc, raw);
           tmem_ld_wait();
-          const uint8_t* sl = slab[rseq & 1];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {   // 8 columns: 16 bytes of hi + 16 bytes of lo
-            float r[8];
-            join_hi_lo8(*reinterpret_cast<const uint4*>(sl + slab64_off(lane, j)),
-                        *reinterpret_cast<const uint4*>(sl + 2048 + slab64_off(lane, j)), r);
-            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + 32 * c + 8 * j);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 32 * c + 8 * j + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          for (int hh = 0; hh < 2; ++hh) {
+            const int c = 2 * cc + hh;
+            mbar_wait(&rb[rseq & 1], (rseq >> 1) & 1);
+            const uint8_t* sl = slab[rseq & 1];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float v = r[i] + (__uint_as_float(raw[8 * j + i]) + bb[i]);
-              sum += v;
-              sumsq = fmaf(v, v, sumsq);
-              raw[8 * j + i] = __float_as_uint(v);
+            for (int j = 0; j < 4; ++j) {   // 8 columns: 16 bytes of hi + 16 bytes of lo
+              float r[8];
+              join_hi_lo8(*reinterpret_cast<const uint4*>(sl + slab64_off(lane, j)),
+                          *reinterpret_cast<const uint4*>(sl + 2048 + slab64_off(lane, j)), r);
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + 32 * c + 8 * j);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 32 * c + 8 * j + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float v = r[i] + (__uint_as_float(raw[32 * hh + 8 * j + i]) + bb[i]);
+                sum += v;
+                sumsq = fmaf(v, v, sumsq);
+                raw[32 * hh + 8 * j + i] = __float_as_uint(v);
+              }
             }
+            __syncwarp();
+            if (c + 2 < 4) load_resid(rseq + 2, c + 2);
+            ++rseq;
+            if (tr) tr[tri++] = clock64();
           }
-          tmem_st_32x32(taddr + 32 * c, raw);
-          __syncwarp();
-          if (c + 2 < 4) load_resid(rseq + 2, c + 2);
-          ++rseq;
-          if (tr) tr[tri++] = clock64();
+          tmem_st_32x64(taddr + 64 * cc, raw);
         }
         tmem_st_wait();
       }
@@ -264,10 +269,14 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (lane == 0) bulk_wait_group_read<0>();
         __syncwarp();
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t raw[32];
-          tmem_ld_32x32(taddr + 32 * c, raw);
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t raw64[64];
+          tmem_ld_32x64(taddr + 64 * cc, raw64);
           tmem_ld_wait();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+          const int c = 2 * cc + hh;
+          const uint32_t* raw = raw64 + 32 * hh;
           uint8_t* o32 = slab[c & 1];
           if (c >= 2) {
             if (lane == 0) bulk_wait_group_read<1>();
@@ -297,6 +306,7 @@ gemm_resid_ln_cluster(const __grid_constant__ CUtensorMap map_a, const __grid_co
             bulk_commit_group();
           }
           if (tr) tr[tri++] = clock64();
+          }
         }
       }
       tc_fence_before();

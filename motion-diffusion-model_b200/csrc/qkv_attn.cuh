@@ -301,25 +301,25 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_con
       const float inv = tot > 0.f ? 1.f / tot : 0.f;
       {
         const uint32_t tO = trow + 384 + 64 * part;
-        uint32_t ra[32], rb[32];
-        tmem_ld_32x32(tO, ra);
-        tmem_ld_32x32(tO + 32, rb);
+        uint32_t ro[64];
+        tmem_ld_32x64(tO, ro);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(tmem_free_leader);   // the accumulator columns may be overwritten
-        auto store_o = [&](const uint32_t (&r)[32], int c) {
+        auto store_o = [&](int c) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint32_t w0 = pack_half2(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
-            const uint32_t w1 = pack_half2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
-            const uint32_t w2 = pack_half2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
-            const uint32_t w3 = pack_half2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+            const uint32_t* r = ro + 32 * c + 8 * j;
+            const uint32_t w0 = pack_half2(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+            const uint32_t w1 = pack_half2(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+            const uint32_t w2 = pack_half2(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+            const uint32_t w3 = pack_half2(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
             *reinterpret_cast<uint4*>(o_slab + slab_off(lane, c * 4 + j)) = make_uint4(w0, w1, w2, w3);
           }
         };
-        store_o(ra, 0);
-        store_o(rb, 1);
+        store_o(0);
+        store_o(1);
       }
       fence_proxy_async_smem();
       __syncwarp();
