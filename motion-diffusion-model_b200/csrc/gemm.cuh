@@ -63,13 +63,9 @@ struct EpiCtx {
   bool primed;          // functor-defined: a prefetch for the chunk about to be processed is already in flight
 };
 
-// One tile's epilogue for one warp: chunks c = 64*part, 64*part+32, 64*part+128, ... of the BLOCK_N accumulator
-// columns.  tcgen05.ld of the next chunk is issued before the current chunk is processed (register double buffer);
-// `release` (accumulator free) runs as soon as this warp's last TMEM read has landed.
-template <int BLOCK_N>
-__device__ __forceinline__ int epi_next_chunk(int c) {
-  return ((c & 32) == 0 && c + 32 < BLOCK_N) ? c + 32 : (c & ~63) + 64 * GEMM_EPI_PARTS;
-}
+// One tile's epilogue for one warp: 64-column blocks c = 64*part, 64*part + 64*PARTS, ... of the BLOCK_N accumulator
+// columns, each pulled with one tcgen05.ld and handed to the functor as two 32-column chunks; `release` (accumulator
+// free) runs as soon as this warp's last TMEM read has landed.
 template <int BLOCK_N, class Epi, class Release>
 __device__ __forceinline__ void epilogue_tile(EpiCtx& ctx, const typename Epi::Params& ep, uint32_t taddr, int row0,
                                               int col_base, int part, uint64_t* acc_full_bar, uint32_t acc_phase,

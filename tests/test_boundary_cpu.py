@@ -140,3 +140,26 @@ def test_c_abi_error_contract_without_gpu():
         assert fn.argtypes is not None
     assert lib.b200mdm_set_prefix(None, None, None) < 0
     assert lib.b200mdm_version() >= 1
+
+
+def test_alias_submodules_are_the_same_objects():
+    """`from b200mdm.utils.sampler_util import X` must hand out the package's own class object (a second copy of
+    the module tree made engine_for() unwrap a guidance wrapper down to the bare denoiser, silently dropping CFG)."""
+    import importlib
+    import b200mdm
+    from b200mdm.utils.sampler_util import ClassifierFreeSampleModel as A
+    from b200mdm.diffusion.respace import SpacedDiffusion as S_
+    import b200mdm.model.mdm as m1
+    assert A is b200mdm.ClassifierFreeSampleModel and S_ is b200mdm.SpacedDiffusion
+    assert m1 is importlib.import_module("motion-diffusion-model_b200.model.mdm")
+
+
+def test_engine_for_rejects_foreign_wrappers():
+    """A wrapper class this package does not know (here: something with a `.model` attribute) is not looked through."""
+    from types import SimpleNamespace
+    import pytest
+    import b200mdm
+    from b200mdm.model.mdm import engine_for
+    model, _ = b200mdm.create_model_and_diffusion(default_args(layers=1), SimpleNamespace(dataset=SimpleNamespace()))
+    with pytest.raises(TypeError):
+        engine_for(SimpleNamespace(model=model))

@@ -139,3 +139,27 @@ def test_dip_two_rank_sharded_run_equals_unsharded(tmp_path):
                                      noise_mode="global", seed=78, device=torch.device("cpu"))
     assert sharded.shape == (B, 263, 1, PRED)
     assert torch.allclose(sharded, single, rtol=0, atol=5e-5)
+
+
+def test_sample_sharded_rejects_batch_smaller_than_world(monkeypatch):
+    """a rank with an empty shard used to raise before the all_gather and hang the others."""
+    import pytest
+    import torch.distributed as dist
+    monkeypatch.setattr(dist, "is_initialized", lambda: True)
+    monkeypatch.setattr(dist, "get_world_size", lambda group=None: 4)
+    monkeypatch.setattr(dist, "get_rank", lambda group=None: 3)
+    with pytest.raises(ValueError):
+        parallel.sample_sharded(lambda *a, **k: None, None, (2, 263, 1, 8), {"y": {}}, n_steps=3)
+
+
+def test_sample_sharded_philox_mode_passes_global_sample_index():
+    """noise_mode='philox' (default): nothing is drawn on the host; the sampler receives the seed and the global index of
+    the shard's first sample, which is what keys the engine's noise stream (G GPUs == 1 GPU, bit for bit)."""
+    seen = {}
+
+    def fn(model, shape, model_kwargs, noise_seed, sample_index_base, **kw):
+        seen.update(shape=shape, seed=noise_seed, base=sample_index_base, B=model_kwargs["y"]["lengths"].shape[0])
+        return torch.zeros(shape)
+    y = {"lengths": torch.arange(5), "text_embed": torch.zeros(1, 5, 512)}
+    out = parallel.sample_sharded(fn, None, (5, 263, 1, 8), {"y": y}, n_steps=3, seed=42, device=torch.device("cpu"))
+    assert seen == dict(shape=(5, 263, 1, 8), seed=42, base=0, B=5) and out.shape == (5, 263, 1, 8)
