@@ -311,7 +311,7 @@ static int launch_gemm2(const CUtensorMap& a, const CUtensorMap& b, const CUtens
   const int tiles = ((M + GEMM2_TILE_M - 1) / GEMM2_TILE_M) * ((N + GEMM2_BLOCK_N - 1) / GEMM2_BLOCK_N);
   const int max_clusters = num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  CUDA_TRY(launch_k(gemm2_f16_tcgen05<Epi>, dim3(2 * clusters), dim3(GEMM_THREADS), Gemm2Smem<Epi>::TOTAL, s, a, b, c, M, N, K, p));
+  CUDA_TRY(launch_k(gemm2_f16_tcgen05<Epi>, dim3(2 * clusters), dim3(GEMM2_THREADS), Gemm2Smem<Epi>::TOTAL, s, a, b, c, M, N, K, p));
   return B200MDM_OK;
 }
 
@@ -361,6 +361,22 @@ static int launch_qkv_attention(const CUtensorMap& h3, const CUtensorMap& w128, 
                     n_samples, S, scale_log2));
   return B200MDM_OK;
 }
+#ifdef B200_TRACE
+// Instrumented build only (lib/libb200mdm_trace.so): B200MDM_DEBUG_SKIP is a bit mask of layer kernels to leave out of the
+// step (1 attention, 2 out-proj+LN, 4 FFN-up, 8 FFN-down+LN) -- the results are garbage, the loop time difference is what
+// that kernel costs INSIDE the graph loop (programmatic dependent launch, L2 window), which no profiler shows.
+static int debug_skip_mask() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200MDM_DEBUG_SKIP");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+#define B200_SKIP(bit) (debug_skip_mask() & (bit))
+#else
+#define B200_SKIP(bit) (0)
+#endif
 static bool fused_qkv_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -974,7 +990,9 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
   const bool wide = kw == 2;
   for (int l = 0; l < e->L; ++l) {
     const LayerW& w = e->layers[l];
-    if (!wide && fused_qkv_enabled()) {
+    if (B200_SKIP(1)) {
+      ++nk;
+    } else if (!wide && fused_qkv_enabled()) {
       // QKV projection + attention in one kernel: the [M, 1536] qkv tensor never exists
       TRY(launch_qkv_attention(e->m_h3, w.m_wqkv, w.m_wqkv_64, e->m_att_o, w.bqkv, e->kvlen, e->Bp, S, s, e->num_sms));
       --nk;
@@ -989,7 +1007,7 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
       AttnMaps am{e->m_att_q, e->m_att_kv, e->m_att_o};
       TRY(launch_attention_tc(am, e->kvlen, e->Bp, S, d, e->H, s, wide));
     }
-    TRY(launch_gemm_resid_ln(e->m_att, w.m_wo_256, e->m_res, e->M, kw * d, w.bo, w.g1, w.be1, s, e->num_sms));
+    if (!B200_SKIP(2)) TRY(launch_gemm_resid_ln(e->m_att, w.m_wo_256, e->m_res, e->M, kw * d, w.bo, w.g1, w.be1, s, e->num_sms));
     if (e->dec) {
       // cross-attention block of nn.TransformerDecoderLayer: q from the sequence, k/v from the text memory
       {
@@ -1008,11 +1026,11 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
     if (wide) {
       EpiBiasF16Wide<true>::Params p{w.b1, ff};
       TRY((launch_gemm2<EpiBiasF16Wide<true>>(e->m_h16, w.m_w1, e->m_ffn_st, e->M, ff, kw * d, p, s, e->num_sms)));
-    } else {
+    } else if (!B200_SKIP(4)) {
       EpiBiasF16<true>::Params p{w.b1};
       TRY((launch_gemm2<EpiBiasF16<true>>(e->m_h16, w.m_w1, e->m_ffn_st, e->M, ff, d, p, s, e->num_sms)));
     }
-    TRY(launch_gemm_resid_ln(e->m_ffn, w.m_w2_256, e->m_res, e->M, kw * ff, w.b2, e->dec ? w.g3 : w.g2,
+    if (!B200_SKIP(8)) TRY(launch_gemm_resid_ln(e->m_ffn, w.m_w2_256, e->m_res, e->M, kw * ff, w.b2, e->dec ? w.g3 : w.g2,
                              e->dec ? w.be3 : w.be2, s, e->num_sms));
     nk += 5;
   }

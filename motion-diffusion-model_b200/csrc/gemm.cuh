@@ -30,7 +30,7 @@ constexpr int GEMM_EPI_WARPS = B200_GEMM_EPI_WARPS;
 constexpr int GEMM_EPI_PARTS = GEMM_EPI_WARPS / 4;
 static_assert(GEMM_EPI_WARPS == 4 || GEMM_EPI_WARPS == 8, "4 or 8 epilogue warps");
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
-constexpr int GEMM_BAR_BYTES = 512;
+constexpr int GEMM_BAR_BYTES = 1024;
 constexpr int GEMM_BIAS_BYTES = 8192;   // per-column epilogue vector (bias) of the whole GEMM, staged once per CTA: N <= 2048
 
 template <int BLOCK_N, class Epi>
@@ -66,7 +66,7 @@ struct EpiCtx {
 // One tile's epilogue for one warp: 64-column blocks c = 64*part, 64*part + 64*PARTS, ... of the BLOCK_N accumulator
 // columns, each pulled with one tcgen05.ld and handed to the functor as two 32-column chunks; `release` (accumulator
 // free) runs as soon as this warp's last TMEM read has landed.
-template <int BLOCK_N, class Epi, class Release>
+template <int BLOCK_N, class Epi, int PARTS = GEMM_EPI_PARTS, class Release>
 __device__ __forceinline__ void epilogue_tile(EpiCtx& ctx, const typename Epi::Params& ep, uint32_t taddr, int row0,
                                               int col_base, int part, uint64_t* acc_full_bar, uint32_t acc_phase,
                                               Release release) {
@@ -92,9 +92,9 @@ __device__ __forceinline__ void epilogue_tile(EpiCtx& ctx, const typename Epi::P
   // while the MMAs of tile i+1 own the TMEM port, which arbitrates per instruction -- fewer, wider loads wait less.
   uint32_t raw[64];
 #pragma unroll 1
-  for (int c = part * 64; c < BLOCK_N; c += 64 * GEMM_EPI_PARTS) {
+  for (int c = part * 64; c < BLOCK_N; c += 64 * PARTS) {
     const bool two = c + 32 < BLOCK_N;                       // (BLOCK_N = 96: the last block is a single chunk)
-    const int cnext = c + 64 * GEMM_EPI_PARTS;
+    const int cnext = c + 64 * PARTS;
     if (two) tmem_ld_32x64(taddr + c, raw);
     else tmem_ld_32x32(taddr + c, *reinterpret_cast<uint32_t(*)[32]>(raw));
     tmem_ld_wait();

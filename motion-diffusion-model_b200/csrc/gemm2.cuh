@@ -30,6 +30,11 @@ __device__ long long* g_gemm2_trace = nullptr;
 #define B200_TRACE_PTR(cond, ptr) (static_cast<long long*>(nullptr))
 #endif
 
+#ifndef B200_GEMM2_EPI_WARPS
+#define B200_GEMM2_EPI_WARPS 8
+#endif
+constexpr int GEMM2_EPI_WARPS = B200_GEMM2_EPI_WARPS;   // 8 or 16 (4 lane quarters x 2 or 4 column parts)
+constexpr int GEMM2_THREADS = 64 + 32 * GEMM2_EPI_WARPS;
 constexpr int GEMM2_BLOCK_N = 256;   // per pair: 256 x 256 output tile; per CTA: 128 rows x 256 columns of accumulator
 constexpr int GEMM2_TILE_M = 256;
 
@@ -38,7 +43,7 @@ struct Gemm2Smem {
   static constexpr int A_BYTES = 128 * GEMM_BLOCK_K * 2;  // this CTA's 128 rows of A
   static constexpr int B_BYTES = 128 * GEMM_BLOCK_K * 2;  // this CTA's half (128 rows) of the W tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KB
-  static constexpr int EPI_BYTES = GEMM_EPI_WARPS * Epi::SMEM_PER_WARP;
+  static constexpr int EPI_BYTES = GEMM2_EPI_WARPS * Epi::SMEM_PER_WARP;
   static constexpr int budget = 227 * 1024 - 1024 - EPI_BYTES - GEMM_BIAS_BYTES - GEMM_BAR_BYTES;
   static constexpr int STAGES = (budget / STAGE_BYTES) > 6 ? 6 : (budget / STAGE_BYTES);
   static constexpr int TOTAL = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + GEMM_BIAS_BYTES + GEMM_BAR_BYTES;
@@ -46,7 +51,7 @@ struct Gemm2Smem {
 };
 
 template <class Epi>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
 gemm2_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_c, int M, int N, int K,
                   const __grid_constant__ typename Epi::Params ep) {
@@ -65,8 +70,9 @@ gemm2_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]  (each CTA waits on its own)
   uint64_t* acc_full = bars + 2 * STAGES;       // [2]       (each CTA waits on its own)
   uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]       (leader's copy is the live one)
-  uint64_t* epi_bars = bars + 2 * STAGES + 4;   // [GEMM_EPI_WARPS][4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bars + GEMM_EPI_WARPS * 4);
+  uint64_t* epi_bars = bars + 2 * STAGES + 4;   // [GEMM2_EPI_WARPS][4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_bars + GEMM2_EPI_WARPS * 4);
+  static_assert((2 * 6 + 4 + GEMM2_EPI_WARPS * 4) * 8 + 8 <= GEMM_BAR_BYTES, "barrier area too small");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -91,9 +97,9 @@ gemm2_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);                     // one multicast commit
-      mbar_init(&acc_empty[s], 2 * GEMM_EPI_WARPS);   // the epilogue warps of both CTAs
+      mbar_init(&acc_empty[s], 2 * GEMM2_EPI_WARPS);   // the epilogue warps of both CTAs
     }
-    for (int s = 0; s < GEMM_EPI_WARPS * 4; ++s) mbar_init(&epi_bars[s], 1);
+    for (int s = 0; s < GEMM2_EPI_WARPS * 4; ++s) mbar_init(&epi_bars[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -188,7 +194,7 @@ gemm2_f16_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       if (tr) tr[4] = clock64();
       if (tr) { mbar_wait(&acc_full[as], aphase); tr[5] = clock64(); }
       ctx.trace = (tr && it >= 2 && it < 6) ? g_gemm2_trace + 64 + (it - 2) * 16 : nullptr;
-      epilogue_tile<GEMM2_BLOCK_N, Epi>(ctx, ep, taddr, row0, n_blk * GEMM2_BLOCK_N, part, &acc_full[as], aphase, [&]() {
+      epilogue_tile<GEMM2_BLOCK_N, Epi, GEMM2_EPI_WARPS / 4>(ctx, ep, taddr, row0, n_blk * GEMM2_BLOCK_N, part, &acc_full[as], aphase, [&]() {
         if (leader) mbar_arrive(&acc_empty[as]);
         else mbar_arrive_remote_relaxed(mapa_shared(smem_u32(&acc_empty[as]), 0));
       });
