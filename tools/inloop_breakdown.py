@@ -20,6 +20,10 @@ def loop_ms(mask):
     return float(m.group(1)) if m else float("nan")
 
 
+if not os.path.exists(LIB):
+    sys.path.insert(0, ROOT)
+    import importlib
+    importlib.import_module("motion-diffusion-model_b200.build").build(trace=True)
 base = loop_ms(0)
 print("%-40s %8.2f ms per 50-step loop  (%.0f us per step)" % (NAMES[0], base, base * 20))
 for mask in (1, 2, 4, 8, 15):

@@ -2,6 +2,13 @@ import ctypes, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("B200MDM_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "motion-diffusion-model_b200", "lib", "libb200mdm_trace.so"))   # -DB200_TRACE build: B200MDM_TRACE=1 python -m b200mdm.build
+def _ensure_trace_lib():
+    import importlib
+    if not os.path.exists(os.environ["B200MDM_LIB"]):
+        importlib.import_module("motion-diffusion-model_b200.build").build(trace=True)
+
+
+_ensure_trace_lib()
 from b200mdm import _lib
 lib = _lib.load()
 lib.b200mdm_debug_trace.argtypes = [ctypes.c_void_p]
