@@ -567,7 +567,9 @@ def main():
                     "frac": top["frac"], "us": top["us"], "flop_per_launch": top["flop"],
                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch: taken from the committed ncu
                     # capture, not re-measured per run (a profiler cannot run inside a timed bench)
-                    "traffic": None, "traffic_source": "profiles/r02_*_ncu_metrics.txt",
+                    "traffic": 17.5e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full, "
+                                                        "profiles/r02_f_ncu_qkv_attention_kernel.txt (14.5 MB + 3.0 MB: the operands are "
+                                                        "L2-resident; algorithmic operand bytes 164 MB per launch come from the L2)",
                     "peak_source": peaks["source"] + " bf16 burst (cuBLAS 8192^3)",
                     "other_kernels": [{k: r[k] for k in ("kernel", "achieved", "frac", "us")} for r in rows[1:]]}
             log("kernel roofline timed: %s" % ", ".join("%.0f us" % r["us"] for r in rows))

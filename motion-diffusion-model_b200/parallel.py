@@ -39,6 +39,27 @@ def broadcast_text_embed(text_embed, src=0, group=None):
     return text_embed
 
 
+def shard_replications(replication_times, rank=None, world=None):
+    """Evaluation (eval/eval_humanml.py:262-329 runs the whole generate-and-score pass `replication_times` times, each
+    with its own `CompMDMGeneratedDataset`): replications are independent, so rank r takes replications
+    r, r + world, ... and the per-replication metrics are gathered afterwards (`gather_objects`).  No traffic between the
+    ranks while a replication runs."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    return list(range(rank, replication_times, world))
+
+
+def gather_objects(obj, group=None):
+    """All ranks' python objects (e.g. {replication index: metrics dict}) on every rank, in rank order."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return [obj]
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, obj, group=group)
+    return out
+
+
 _BATCH_KEYS = ("mask", "lengths", "scale", "action", "inpainting_mask", "inpainted_motion", "prefix")
 
 

@@ -163,3 +163,12 @@ def test_sample_sharded_philox_mode_passes_global_sample_index():
     y = {"lengths": torch.arange(5), "text_embed": torch.zeros(1, 5, 512)}
     out = parallel.sample_sharded(fn, None, (5, 263, 1, 8), {"y": y}, n_steps=3, seed=42, device=torch.device("cpu"))
     assert seen == dict(shape=(5, 263, 1, 8), seed=42, base=0, B=5) and out.shape == (5, 263, 1, 8)
+
+
+def test_shard_replications_partition():
+    """eval_humanml's replications split over ranks: disjoint, complete, round-robin."""
+    for n, world in ((20, 8), (5, 8), (3, 1), (7, 2)):
+        parts = [parallel.shard_replications(n, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(n))
+        assert all(p == list(range(r, n, world)) for r, p in enumerate(parts))
+    assert parallel.gather_objects({"a": 1}) == [{"a": 1}]
