@@ -25,6 +25,10 @@ class _AliasLoader(importlib.abc.Loader):
     def exec_module(self, module):                           # already executed under its real name
         pass
 
+    def get_code(self, fullname):                            # runpy (`python -m b200mdm.build`) asks for this
+        spec = importlib.util.find_spec(self.real_name)
+        return spec.loader.get_code(self.real_name)
+
 
 class _AliasFinder(importlib.abc.MetaPathFinder):
     def find_spec(self, fullname, path=None, target=None):
@@ -37,7 +41,9 @@ class _AliasFinder(importlib.abc.MetaPathFinder):
             return None
         if real_spec is None:
             return None
-        spec = importlib.util.spec_from_loader(fullname, _AliasLoader(real), is_package=real_spec.submodule_search_locations is not None)
+        spec = importlib.util.spec_from_loader(fullname, _AliasLoader(real), origin=real_spec.origin,
+                                               is_package=real_spec.submodule_search_locations is not None)
+        spec.has_location = real_spec.has_location
         return spec
 
 

@@ -692,7 +692,7 @@ static int build_workspace(b200mdm_engine* e, int B, int T, int halves, cudaStre
   if (need_qkv) TRY(dalloc(&e->qkv16, M * 3 * d));
   TRY(dalloc(&e->att16, M * d * kw));
   TRY(dalloc(&e->ffn16, M * e->ff * kw));
-  TRY(dalloc(&e->g16, MB * 3 * d));
+  TRY(dalloc(&e->g16, static_cast<size_t>(B) * T * 3 * d));           // frame rows only
   TRY(dalloc(&e->tok0, static_cast<size_t>(Bp) * d));
   TRY(dalloc(&e->condproj, static_cast<size_t>(Bp) * d, true));
   TRY(dalloc(&e->proj, static_cast<size_t>(B) * d, true));
@@ -715,7 +715,7 @@ static int build_workspace(b200mdm_engine* e, int B, int T, int halves, cudaStre
   TRY(make_map(&e->m_h16, e->hres, M, kw * d, 2 * d, GEMM_BLOCK_M));
   TRY(make_map(&e->m_att, e->att16, M, kw * d, kw * d, GEMM_BLOCK_M));
   TRY(make_map(&e->m_ffn, e->ffn16, M, kw * e->ff, kw * e->ff, GEMM_BLOCK_M));
-  TRY(make_map(&e->m_g16, e->g16, MB, 3 * d, 3 * d, GEMM_BLOCK_M));
+  TRY(make_map(&e->m_g16, e->g16, static_cast<size_t>(B) * T, 3 * d, 3 * d, GEMM_BLOCK_M));
   if (need_qkv) TRY(make_map_t(&e->m_qkv_st, e->qkv16, 2, M, 3 * d, 3 * d, 32));
   TRY(make_map_t(&e->m_ffn_st, e->ffn16, 2, M, kw * e->ff, kw * e->ff, 32));
   TRY(make_map_res(&e->m_res, e->hres, M, d));
@@ -1034,7 +1034,8 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
                              e->dec ? w.be3 : w.be2, s, e->num_sms));
     nk += 5;
   }
-  CUDA_TRY(launch_k(blend_split_kernel, dim3((e->MB + 7) / 8), dim3(256), 0, s, e->hres, e->g16, e->scale, B, S, d, e->halves));
+  CUDA_TRY(launch_k(blend_split_kernel, dim3((B * T + 7) / 8), dim3(256), 0, s, e->hres, e->g16, e->scale, B, S, T, e->s_off, d,
+                    e->halves));
   ++nk;
   {
     EpiOutStep::Params p;
@@ -1048,10 +1049,10 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
     p.sched = e->sched;
     p.state = e->state;
     p.noise_batch_stride = a.const_noise ? 0 : static_cast<long long>(JF) * T;
-    p.B = B; p.S = S; p.T = T; p.J = JF; p.mode = a.mode;
-    p.s_off = e->s_off;
+    p.B = B; p.S = T; p.T = T; p.J = JF; p.mode = a.mode;      // g16 rows are frames: row = b*T + t
+    p.s_off = 0;
     p.clip_denoised = a.clip;
-    TRY((launch_gemm<96, EpiOutStep>(e->m_g16, e->m_wout, e->m_g16, e->MB, e->N_out_pad, 3 * d, p, s, e->num_sms)));
+    TRY((launch_gemm<96, EpiOutStep>(e->m_g16, e->m_wout, e->m_g16, B * T, e->N_out_pad, 3 * d, p, s, e->num_sms)));
     ++nk;
   }
   *n_kernels = nk;

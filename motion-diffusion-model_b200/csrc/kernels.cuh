@@ -151,17 +151,20 @@ __global__ void philox_normal_kernel(float* __restrict__ out, int B, long long n
 //   OutputProcess: W(h_u + s(h_c-h_u)) + b == out_u + s(out_c - out_u) exactly in real arithmetic)
 //   halves == 1: v = h.       g16 row layout: [hi | lo | hi], ld = 3*d.
 __global__ void blend_split_kernel(const __half* __restrict__ hres, __half* __restrict__ g16,
-                                   const float* __restrict__ scale, int B, int S, int d, int halves) {
+                                   const float* __restrict__ scale, int B, int S, int T, int s_off, int d, int halves) {
   pdl_launch_dependents();
   pdl_wait();
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // one warp per FRAME row: the rows s < s_off of a sequence (condition token / DiP prefix) never reach x, so g16
+  // holds B*T rows only (12544 = 98 tiles of 128 at B=64, T=196 -- 294 output tiles, two full waves of 148 CTAs)
+  const int orow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= B * S) return;
-  const int b = row / S;
+  if (orow >= B * T) return;
+  const int b = orow / T;
+  const int row = b * S + s_off + (orow - b * T);
   const __half* hc = hres + static_cast<size_t>(row) * 2 * d;                         // [hi | lo] rows
   const __half* hu = hres + (static_cast<size_t>(B) * S + row) * 2 * d;
   const float sc = (halves == 2) ? scale[b] : 0.f;
-  __half* dst = g16 + static_cast<size_t>(row) * 3 * d;
+  __half* dst = g16 + static_cast<size_t>(orow) * 3 * d;
   for (int c = lane * 2; c < d; c += 64) {
     const float2 ah = __half22float2(*reinterpret_cast<const __half2*>(hc + c));
     const float2 al = __half22float2(*reinterpret_cast<const __half2*>(hc + d + c));
