@@ -194,6 +194,12 @@ int b200mdm_test_gemm_f16(const void* a16_dev, const void* w16_dev, const float*
  * impl must be 0 (tcgen05 kernel, S <= 256). */
 int b200mdm_test_attention(const void* qkv16_dev, void* out16_dev, const int32_t* kvlen_dev, int32_t n_samples,
                            int32_t S, int32_t d, int32_t impl, void* stream);
+/* Cross-attention core of the trans_dec (DiP) layers, nn.MultiheadAttention(query = sequence, key = value = text memory)
+ * between its in- and out-projections (model/mdm.py:219-224 via nn.TransformerDecoderLayer): d = 512, 4 heads.
+ * q16 fp16 [n*S, 512]; kv16 fp16 rows (sample, token) of pitch ld_kv >= 1024 holding k | v; mask uint8 [n, n_tokens]
+ * (1 = padding token); out16 fp16 [n*S, 1024]: columns [0, 512) are written.  n_tokens <= 64. */
+int b200mdm_test_cross_attention(const void* q16_dev, const void* kv16_dev, const unsigned char* mask_dev, void* out16_dev,
+                                 int32_t n_samples, int32_t S, int32_t n_tokens, int32_t ld_kv, void* stream);
 /* The fused QKV-projection + attention kernel of the encoder layers (nn.MultiheadAttention up to its output projection,
  * model/mdm.py:77-84): out16[n*S, 512] = concat_h softmax((h Wq_h^T + bq)(h Wk_h^T + bk)^T / sqrt(128) + mask)(h Wv_h^T + bv).
  * h16: fp16 [n*S, ld] (first 512 columns used), wqkv16: in_proj_weight fp16 [1536, 512], bqkv fp32 [1536],

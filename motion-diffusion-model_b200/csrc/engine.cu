@@ -129,9 +129,9 @@ struct LayerW {
   CUtensorMap m_wqkv_64;                  // box 64 rows: the V half-tiles of the fused QKV + attention kernel
   CUtensorMap m_wo_256, m_w2_256;         // box 256 rows: residual+LayerNorm kernel (each CTA owns 256 output columns)
   // trans_dec only: cross-attention (multihead_attn) projections and the third LayerNorm
-  __half *wq_c = nullptr, *wkv_c = nullptr, *wo_c = nullptr;
-  const float *bq_c = nullptr, *bkv_c = nullptr, *bo_c = nullptr, *g3 = nullptr, *be3 = nullptr;
-  CUtensorMap m_wq_c, m_wkv_c, m_wo_c_256;
+  __half *wq_c = nullptr, *wo_c = nullptr;           // (the K/V rows of all layers live in engine->wkv_all)
+  const float *bq_c = nullptr, *bo_c = nullptr, *g3 = nullptr, *be3 = nullptr;
+  CUtensorMap m_wq_c, m_wo_c_256;
 };
 
 struct GraphKey {
@@ -186,6 +186,11 @@ struct b200mdm_engine : Workspace {
   std::vector<LayerW> layers;
   const float *b_in = nullptr, *b_out = nullptr, *pe = nullptr, *w_txt = nullptr, *b_txt = nullptr, *act_emb = nullptr;
   float *temb_hidden = nullptr, *temb_table = nullptr;
+  // trans_dec: key/value projection rows of the cross-attention of ALL layers, [L * 2d, d] fp16 + bias [L * 2d]: the text
+  // memory is the same for every layer, so one GEMM per step projects it for all of them
+  __half* wkv_all = nullptr;
+  float* bkv_all = nullptr;
+  CUtensorMap m_wkv_all;
   // schedule (device tables are allocated once at `sched_cap` rows: the step graphs hold these pointers)
   float* sched = nullptr;
   int* tmap = nullptr;
@@ -247,6 +252,7 @@ static int init_kernel_attrs() {
   TRY((set_gemm2_attr<EpiBiasF16<false>>()));
   TRY((set_gemm2_attr<EpiBiasF16<true>>()));
   TRY((set_gemm2_attr<EpiBiasF16Wide<true>>()));
+  TRY((set_gemm2_attr<EpiBiasF16Global>()));
   CUDA_TRY(cudaFuncSetAttribute(gemm_resid_ln_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLnSmem::TOTAL));
   TRY((set_gemm_attr<128, EpiEmbed>()));
   TRY((set_gemm_attr<96, EpiOutStep>()));
@@ -304,10 +310,13 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
 }
 
 // CTA-pair GEMM (256 x 256 tiles): a = A map (box 128 rows), b = W map with box 128 rows (half tile per CTA)
+template <class Epi, class = void> struct epi_unstaged : std::false_type {};
+template <class Epi> struct epi_unstaged<Epi, std::enable_if_t<Epi::UNSTAGED>> : std::true_type {};
+
 template <class Epi>
 static int launch_gemm2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int M, int N, int K,
                         const typename Epi::Params& p, cudaStream_t s, int num_sms) {
-  if (N * 4 > GEMM_BIAS_BYTES) return fail(B200MDM_ENOTIMPL, "GEMM epilogue vectors are staged for N <= %d", GEMM_BIAS_BYTES / 4);
+  if (!epi_unstaged<Epi>::value && N * 4 > GEMM_BIAS_BYTES) return fail(B200MDM_ENOTIMPL, "GEMM epilogue vectors are staged for N <= %d", GEMM_BIAS_BYTES / 4);
   const int tiles = ((M + GEMM2_TILE_M - 1) / GEMM2_TILE_M) * ((N + GEMM2_BLOCK_N - 1) / GEMM2_BLOCK_N);
   const int max_clusters = num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
@@ -464,8 +473,9 @@ extern "C" int b200mdm_destroy(b200mdm_engine* e) {
   cudaDeviceSynchronize();
   free_all_workspaces(e);
   for (auto& kv : e->store) cudaFree(kv.second.dev);
-  for (auto& l : e->layers) { dfree(l.wqkv); dfree(l.wo); dfree(l.w1); dfree(l.w2); dfree(l.wq_c); dfree(l.wkv_c); dfree(l.wo_c); }
+  for (auto& l : e->layers) { dfree(l.wqkv); dfree(l.wo); dfree(l.w1); dfree(l.w2); dfree(l.wq_c); dfree(l.wo_c); }
   dfree(e->w_in3); dfree(e->w_out3); dfree(e->temb_hidden); dfree(e->temb_table); dfree(e->sched); dfree(e->tmap);
+  dfree(e->wkv_all); dfree(e->bkv_all);
   dfree(e->state);
   if (e->work) cudaStreamDestroy(e->work);
   if (e->ev_in) cudaEventDestroy(e->ev_in);
@@ -577,8 +587,8 @@ extern "C" int b200mdm_finalize_weights(b200mdm_engine* e, void* stream) {
   // the next one
   CUDA_TRY(cudaDeviceSynchronize());
   free_all_workspaces(e);
-  for (auto& l : e->layers) { dfree(l.wqkv); dfree(l.wo); dfree(l.w1); dfree(l.w2); dfree(l.wq_c); dfree(l.wkv_c); dfree(l.wo_c); }
-  dfree(e->w_in3); dfree(e->w_out3); dfree(e->temb_hidden); dfree(e->temb_table);
+  for (auto& l : e->layers) { dfree(l.wqkv); dfree(l.wo); dfree(l.w1); dfree(l.w2); dfree(l.wq_c); dfree(l.wo_c); }
+  dfree(e->w_in3); dfree(e->w_out3); dfree(e->temb_hidden); dfree(e->temb_table); dfree(e->wkv_all); dfree(e->bkv_all);
 
   // split-precision in / out projections: W' = [hi | hi | lo], zero padded
   const int Kp = e->Kp_in;
@@ -629,12 +639,18 @@ extern "C" int b200mdm_finalize_weights(b200mdm_engine* e, void* stream) {
       TRY(need(e, p + "norm3.weight", {d}, &w.g3));
       TRY(need(e, p + "norm3.bias", {d}, &w.be3));
       w.bq_c = bc;
-      w.bkv_c = bc + d;
       TRY(to_f16_k(wc, &w.wq_c, d, d, kw, s));
-      TRY(to_f16_k(wc + static_cast<size_t>(d) * d, &w.wkv_c, 2 * d, d, kw, s));
+      if (l == 0) {
+        TRY(dalloc(&e->wkv_all, static_cast<size_t>(e->L) * 2 * d * d));
+        TRY(dalloc(&e->bkv_all, static_cast<size_t>(e->L) * 2 * d));
+        TRY(make_map(&e->m_wkv_all, e->wkv_all, static_cast<uint64_t>(e->L) * 2 * d, d, d, 128));
+      }
+      f32_to_f16_kernel<<<512, 256, 0, s>>>(wc + static_cast<size_t>(d) * d, e->wkv_all + static_cast<size_t>(l) * 2 * d * d,
+                                            static_cast<size_t>(2) * d * d);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaMemcpyAsync(e->bkv_all + static_cast<size_t>(l) * 2 * d, bc + d, sizeof(float) * 2 * d, cudaMemcpyDeviceToDevice, s));
       TRY(to_f16_k(woc, &w.wo_c, d, d, kw, s));
       TRY(make_map(&w.m_wq_c, w.wq_c, d, kw * d, kw * d, 128));
-      TRY(make_map(&w.m_wkv_c, w.wkv_c, 2 * d, kw * d, kw * d, 128));
       TRY(make_map(&w.m_wo_c_256, w.wo_c, d, kw * d, kw * d, 256));
     }
   }
@@ -879,10 +895,10 @@ extern "C" int b200mdm_set_cond_dec(b200mdm_engine* e, int32_t batch, int32_t nf
     TRY(dalloc(&e->memtok, static_cast<size_t>(B) * Mt * d));
     TRY(dalloc(&e->memproj, static_cast<size_t>(Bp) * Mt * d));
     TRY(dalloc(&e->mem16, static_cast<size_t>(Bp) * Mt * 2 * d));   // [hi | lo]
-    TRY(dalloc(&e->kvc16, static_cast<size_t>(Bp) * Mt * 2 * d));
+    TRY(dalloc(&e->kvc16, static_cast<size_t>(Bp) * Mt * 2 * d * e->L));      // [Bp*Mt, L * (k | v)]
     TRY(dalloc(&e->memmask, static_cast<size_t>(Bp) * Mt));
     TRY(make_map(&e->m_mem, e->mem16, static_cast<uint64_t>(Bp) * Mt, 2 * d, 2 * d, GEMM_BLOCK_M));
-    TRY(make_map_t(&e->m_kvc_st, e->kvc16, 2, static_cast<uint64_t>(Bp) * Mt, 2 * d, 2 * d, 32));
+    TRY(make_map_t(&e->m_kvc_st, e->kvc16, 2, static_cast<uint64_t>(Bp) * Mt, 2 * d * e->L, 2 * d * e->L, 32));
     e->Mt = Mt;
   }
   // key mask of the frames: the context frames are always valid (model/mdm.py:204-206), then `lengths` frames of x
@@ -984,6 +1000,10 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
     // cross-attention memory of this step: text tokens + timestep embedding (model/mdm.py:218-220)
     CUDA_TRY(launch_k(mem_build_kernel, dim3(e->Mt, e->Bp), dim3(128), 0, s, e->mem16, e->memproj, e->temb_table,
                       a.explicit_t ? e->tvec : nullptr, e->tmap, e->state, B, e->Mt, d, e->cfg.temb_rows));
+    // ... and its key / value projections for every layer in one GEMM (N = L * 2d; hi half of the memory, K = d)
+    EpiBiasF16Global::Params p{e->bkv_all};
+    TRY((launch_gemm2<EpiBiasF16Global>(e->m_mem, e->m_wkv_all, e->m_kvc_st, e->Bp * e->Mt, e->L * 2 * d, d, p, s, e->num_sms)));
+    ++nk;
   }
   ++nk;
   const int kw = e->kw;
@@ -1015,13 +1035,19 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
         TRY((launch_gemm2<EpiBiasF16<false>>(e->m_h16, w.m_wq_c, e->m_qc_st, e->M, d, d, p, s, e->num_sms)));
       }
       {
-        EpiBiasF16<false>::Params p{w.bkv_c};
-        TRY((launch_gemm2<EpiBiasF16<false>>(e->m_mem, w.m_wkv_c, e->m_kvc_st, e->Bp * e->Mt, 2 * d, d, p, s, e->num_sms)));
+        const float sl2 = 1.4426950408889634f / sqrtf(128.0f);
+        const dim3 cg(e->H, e->Bp), cb(128);
+        const __half* kvl = e->kvc16 + static_cast<size_t>(l) * 2 * d;      // this layer's k | v columns
+        const int ldkv = e->L * 2 * d;
+        if (e->Mt <= 16)
+          CUDA_TRY(launch_k(cross_attention_kernel<2>, cg, cb, 0, s, e->qc16, kvl, e->memmask, e->att16, S, e->Mt, d, ldkv, sl2));
+        else if (e->Mt <= 32)
+          CUDA_TRY(launch_k(cross_attention_kernel<4>, cg, cb, 0, s, e->qc16, kvl, e->memmask, e->att16, S, e->Mt, d, ldkv, sl2));
+        else
+          CUDA_TRY(launch_k(cross_attention_kernel<8>, cg, cb, 0, s, e->qc16, kvl, e->memmask, e->att16, S, e->Mt, d, ldkv, sl2));
       }
-      CUDA_TRY(launch_k(cross_attention_kernel, dim3(e->H, e->Bp), dim3(128), static_cast<size_t>(e->Mt) * 512, s, e->qc16,
-                        e->kvc16, e->memmask, e->att16, S, e->Mt, d, 1.0f / sqrtf(128.0f)));
       TRY(launch_gemm_resid_ln(e->m_att, w.m_wo_c_256, e->m_res, e->M, d, w.bo_c, w.g2, w.be2, s, e->num_sms));   // cross-attention output: hi half
-      nk += 4;
+      nk += 3;
     }
     if (wide) {
       EpiBiasF16Wide<true>::Params p{w.b1, ff};
@@ -1296,6 +1322,25 @@ extern "C" int b200mdm_test_attention(const void* qkv16_dev, void* out16_dev, co
   AttnMaps am;
   TRY(make_attn_maps(&am, static_cast<const __half*>(qkv16_dev), static_cast<__half*>(out16_dev), n_samples, S, d));
   return launch_attention_tc(am, kvlen_dev, n_samples, S, d, d / ATC_DH, s);
+}
+
+extern "C" int b200mdm_test_cross_attention(const void* q16_dev, const void* kv16_dev, const unsigned char* mask_dev,
+                                            void* out16_dev, int32_t n_samples, int32_t S, int32_t n_tokens, int32_t ld_kv,
+                                            void* stream) {
+  const int d = 512;
+  if (!q16_dev || !kv16_dev || !mask_dev || !out16_dev || n_samples <= 0 || S <= 0 || n_tokens <= 0 || n_tokens > 64 ||
+      ld_kv < 2 * d || ld_kv % 8)
+    return fail(B200MDM_EINVAL, "bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const float sl2 = 1.4426950408889634f / sqrtf(128.0f);
+  const dim3 cg(d / 128, n_samples), cb(128);
+  const __half* q = static_cast<const __half*>(q16_dev);
+  const __half* kv = static_cast<const __half*>(kv16_dev);
+  __half* o = static_cast<__half*>(out16_dev);
+  if (n_tokens <= 16) CUDA_TRY(launch_k(cross_attention_kernel<2>, cg, cb, 0, s, q, kv, mask_dev, o, S, n_tokens, d, ld_kv, sl2));
+  else if (n_tokens <= 32) CUDA_TRY(launch_k(cross_attention_kernel<4>, cg, cb, 0, s, q, kv, mask_dev, o, S, n_tokens, d, ld_kv, sl2));
+  else CUDA_TRY(launch_k(cross_attention_kernel<8>, cg, cb, 0, s, q, kv, mask_dev, o, S, n_tokens, d, ld_kv, sl2));
+  return B200MDM_OK;
 }
 
 extern "C" int b200mdm_test_qkv_attention(const void* h16_dev, int32_t ld, const void* wqkv16_dev, const float* bqkv_dev,

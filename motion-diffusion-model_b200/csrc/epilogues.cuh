@@ -109,8 +109,10 @@ struct EpiBiasF16 {
     for (int i = tid; i < N; i += nthreads) dst[i] = p.bias[i];
   }
   static __device__ __forceinline__ void tile_begin(EpiCtx&, const Params&, int, int) {}
-  static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0,
-                                               int) {
+  static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params&, uint32_t (&raw)[32], int row0, int col0, int) {
+    chunk_bias(ctx, ctx.bias_all + col0, raw, row0, col0);   // chunk() is only called for col0 < N, N % 32 == 0 here
+  }
+  static __device__ __forceinline__ void chunk_bias(EpiCtx& ctx, const float* bs, uint32_t (&raw)[32], int row0, int col0) {
     const int half = (col0 >> 5) & 1;
     uint8_t* slab = ctx.smem + (ctx.seq % NSLAB) * 4096;
     if (half == 0) {
@@ -118,7 +120,6 @@ struct EpiBiasF16 {
       if (ctx.lane == 0) bulk_wait_group_read<NSLAB - 1>();
       __syncwarp();
     }
-    const float* bs = ctx.bias_all + col0;   // rows past N are never read: chunk() is only called for col0 < N, N % 32 == 0 here
     uint32_t pk[16];
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -149,6 +150,16 @@ struct EpiBiasF16 {
   static __device__ __forceinline__ void finish(EpiCtx& ctx) {
     if (ctx.lane == 0) bulk_wait_group<0>();
     __syncwarp();
+  }
+};
+
+// EpiBiasF16 for a GEMM wider than the staged-vector limit (the cross-attention K/V projection of all decoder layers
+// at once, N = L * 2d = 8192): the bias is read from global memory per chunk (one broadcast float4 per 4 columns).
+struct EpiBiasF16Global : EpiBiasF16<false> {
+  static constexpr bool UNSTAGED = true;
+  static __device__ __forceinline__ void preload(const Params&, float*, int, int, int) {}
+  static __device__ __forceinline__ void chunk(EpiCtx& ctx, const Params& p, uint32_t (&raw)[32], int row0, int col0, int) {
+    chunk_bias(ctx, p.bias + col0, raw, row0, col0);
   }
 };
 

@@ -316,63 +316,129 @@ __global__ void permute_mbc_kernel(const float* __restrict__ src, float* __restr
 }
 
 // Cross-attention core: softmax(q k^T / sqrt(128) + mask) v with a handful of memory tokens (Mt <= 64).
-//   q16 [n_samples*S, d] (head h at columns h*128), kv16 [n_samples*Mt, 2d] (k | v), mask [n_samples, Mt] (1 = ignore),
-//   out16 [n_samples*S, 2d] = [hi | lo].  One warp per query row, lane owns 4 of the 128 head dimensions.  ~0.5 GFLOP per layer at the
-//   DiP configuration (60 x 16 tokens): CUDA cores are enough, the projections around it run on the tensor cores.
-// grid = (heads, n_samples), block = 128
-__global__ void cross_attention_kernel(const __half* __restrict__ q16, const __half* __restrict__ kv16,
-                                       const unsigned char* __restrict__ mask, __half* __restrict__ out16, int S, int Mt,
-                                       int d, float scale) {
+//   q16 [n_samples*S, d] (head h at columns h*128), kv16 rows (sample, token) of pitch ld_kv holding k | v (v at +d), mask
+//   [n_samples, Mt] (1 = ignore), out16 [n_samples*S, 2d]: the hi half only (the output projection reads K = d).
+// 60 query rows x 16 tokens x 128 per (sample, head): far too small for a 128-row tcgen05 tile and bound by the ~40 MB
+// of q / kv / out traffic, so each warp runs one 16-row m16n8k16 tile straight from registers:
+//   * q and k fragments are read from global memory as 64 contiguous bytes per thread -- a dot product does not care
+//     about the order of its terms, so thread t of a quad owns columns [32t, 32t+32) of the row for BOTH operands;
+//   * softmax on the accumulator fragment (row statistics across the quad with two shuffles), exp2 with the scale
+//     folded in; P is fed back as the A operand of the P.V product in two fp16 terms (hi + lo) so that the
+//     probabilities carry fp32-like precision like the CUDA-core kernel this replaces;
+//   * V is staged transposed in shared memory (pitch padded by 8 halves: conflict-free 32-bit fragment loads).
+// A fully masked row yields 0 (the reference's softmax would give NaN there; it never occurs with a CLS token).
+// grid = (heads, n_samples), block = 128 (4 warps x 16 rows per pass)
+__device__ __forceinline__ void mma_m16n8k16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                             uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t pack_half2_u32(float x, float y) {
+  const __half2 h = __floats2half2_rn(x, y);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int MAX_NT>   // key tiles of 8 tokens: Mt <= 8 * MAX_NT, MAX_NT even
+__global__ void __launch_bounds__(128) cross_attention_kernel(const __half* __restrict__ q16, const __half* __restrict__ kv16,
+                                                              const unsigned char* __restrict__ mask,
+                                                              __half* __restrict__ out16, int S, int Mt, int d, int ld_kv,
+                                                              float scale_log2) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ __half ca_smem[];   // [2][Mt][128]
+  constexpr int KEYS = 8 * MAX_NT, VS = KEYS + 8;
+  __shared__ __align__(16) __half sVt[128 * VS];
+  __shared__ float sBias[KEYS];
   const int h = blockIdx.x, smp = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  __half* sK = ca_smem;
-  __half* sV = ca_smem + Mt * 128;
-  for (int i = threadIdx.x; i < Mt * 16; i += blockDim.x) {   // 16-byte chunks
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const __half* kv = kv16 + static_cast<size_t>(smp) * Mt * ld_kv + h * 128;
+  for (int i = threadIdx.x; i < KEYS * 16; i += 128) {
     const int m = i >> 4, ch = i & 15;
-    const __half* src = kv16 + (static_cast<size_t>(smp) * Mt + m) * 2 * d + h * 128 + ch * 8;
-    *reinterpret_cast<uint4*>(sK + m * 128 + ch * 8) = *reinterpret_cast<const uint4*>(src);
-    *reinterpret_cast<uint4*>(sV + m * 128 + ch * 8) = *reinterpret_cast<const uint4*>(src + d);
-  }
-  __syncthreads();
-  const unsigned char* mk = mask + static_cast<size_t>(smp) * Mt;
-  for (int s = warp; s < S; s += nwarp) {
-    const size_t row = static_cast<size_t>(smp) * S + s;
-    const __half2* qp = reinterpret_cast<const __half2*>(q16 + row * d + h * 128 + lane * 4);
-    const float2 qa = __half22float2(qp[0]), qb = __half22float2(qp[1]);
-    float sc[64];
-    float mx = -INFINITY;
-#pragma unroll 4
-    for (int m = 0; m < Mt; ++m) {
-      const __half2* kp = reinterpret_cast<const __half2*>(sK + m * 128 + lane * 4);
-      const float2 ka = __half22float2(kp[0]), kb = __half22float2(kp[1]);
-      float dot = qa.x * ka.x + qa.y * ka.y + qb.x * kb.x + qb.y * kb.y;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (m < Mt) v = *reinterpret_cast<const uint4*>(kv + static_cast<size_t>(m) * ld_kv + d + ch * 8);
+    const __half* hv = reinterpret_cast<const __half*>(&v);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-      dot = mk[m] ? -INFINITY : dot * scale;
-      sc[m] = dot;
-      mx = fmaxf(mx, dot);
+    for (int j = 0; j < 8; ++j) sVt[(ch * 8 + j) * VS + m] = hv[j];
+  }
+  if (threadIdx.x < KEYS)
+    sBias[threadIdx.x] = (threadIdx.x < Mt && !mask[static_cast<size_t>(smp) * Mt + threadIdx.x]) ? 0.f : -INFINITY;
+  __syncthreads();
+
+  for (int m0 = warp * 16; m0 < S; m0 += 64) {
+    const int r0 = m0 + g, r1 = r0 + 8;
+    const size_t row0 = static_cast<size_t>(smp) * S + min(r0, S - 1), row1 = static_cast<size_t>(smp) * S + min(r1, S - 1);
+    uint32_t qa[16], qb[16];
+    {
+      const uint4* p0 = reinterpret_cast<const uint4*>(q16 + row0 * d + h * 128 + t * 32);
+      const uint4* p1 = reinterpret_cast<const uint4*>(q16 + row1 * d + h * 128 + t * 32);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 a = p0[i], b = p1[i];
+        qa[4 * i] = a.x; qa[4 * i + 1] = a.y; qa[4 * i + 2] = a.z; qa[4 * i + 3] = a.w;
+        qb[4 * i] = b.x; qb[4 * i + 1] = b.y; qb[4 * i + 2] = b.z; qb[4 * i + 3] = b.w;
+      }
     }
-    float sum = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-    for (int m = 0; m < Mt; ++m) {
-      const float p = (mx == -INFINITY) ? 0.f : __expf(sc[m] - mx);
-      sum += p;
-      const __half2* vp = reinterpret_cast<const __half2*>(sV + m * 128 + lane * 4);
-      const float2 va = __half22float2(vp[0]), vb = __half22float2(vp[1]);
-      o0 = fmaf(p, va.x, o0); o1 = fmaf(p, va.y, o1); o2 = fmaf(p, vb.x, o2); o3 = fmaf(p, vb.y, o3);
+    float sc[MAX_NT][4];
+#pragma unroll
+    for (int nt = 0; nt < MAX_NT; ++nt) {
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+      const int key = min(nt * 8 + g, Mt - 1);                        // padded tokens are masked through sBias
+      const uint4* kp = reinterpret_cast<const uint4*>(kv + static_cast<size_t>(key) * ld_kv + t * 32);
+      uint32_t kw[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 a = kp[i];
+        kw[4 * i] = a.x; kw[4 * i + 1] = a.y; kw[4 * i + 2] = a.z; kw[4 * i + 3] = a.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mma_m16n8k16(sc[nt], qa[2 * j], qb[2 * j], qa[2 * j + 1], qb[2 * j + 1], kw[2 * j], kw[2 * j + 1]);
     }
-    const float inv = sum > 0.f ? 1.f / sum : 0.f;
-    o0 *= inv; o1 *= inv; o2 *= inv; o3 *= inv;
-    __half2* op = reinterpret_cast<__half2*>(out16 + row * 2 * d + h * 128 + lane * 4);
-    const __half2 h01 = __floats2half2_rn(o0, o1), h23 = __floats2half2_rn(o2, o3);
-    op[0] = h01;
-    op[1] = h23;
-    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-    __half2* lp = op + d / 2;
-    lp[0] = __floats2half2_rn(o0 - f01.x, o1 - f01.y);
-    lp[1] = __floats2half2_rn(o2 - f23.x, o3 - f23.y);
+    // softmax over the tokens: thread holds tokens nt*8 + 2t, +1 of rows g (c0, c1) and g+8 (c2, c3)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < MAX_NT; ++nt) {
+      const float b0 = sBias[nt * 8 + 2 * t], b1 = sBias[nt * 8 + 2 * t + 1];
+      sc[nt][0] = fmaf(sc[nt][0], scale_log2, b0); sc[nt][1] = fmaf(sc[nt][1], scale_log2, b1);
+      sc[nt][2] = fmaf(sc[nt][2], scale_log2, b0); sc[nt][3] = fmaf(sc[nt][3], scale_log2, b1);
+      mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float off0 = (mx0 == -INFINITY) ? 0.f : mx0, off1 = (mx1 == -INFINITY) ? 0.f : mx1;
+    float sum0 = 0.f, sum1 = 0.f;
+    uint32_t phi[MAX_NT][2], plo[MAX_NT][2];
+#pragma unroll
+    for (int nt = 0; nt < MAX_NT; ++nt) {
+      const float p0 = exp2f(sc[nt][0] - off0), p1 = exp2f(sc[nt][1] - off0);
+      const float p2 = exp2f(sc[nt][2] - off1), p3 = exp2f(sc[nt][3] - off1);
+      sum0 += p0 + p1; sum1 += p2 + p3;
+      const __half2 h01 = __floats2half2_rn(p0, p1), h23 = __floats2half2_rn(p2, p3);
+      const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+      phi[nt][0] = *reinterpret_cast<const uint32_t*>(&h01); phi[nt][1] = *reinterpret_cast<const uint32_t*>(&h23);
+      plo[nt][0] = pack_half2_u32(p0 - f01.x, p1 - f01.y); plo[nt][1] = pack_half2_u32(p2 - f23.x, p3 - f23.y);
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    const float inv0 = (mx0 == -INFINITY || !(sum0 > 0.f)) ? 0.f : 1.f / sum0;
+    const float inv1 = (mx1 == -INFINITY || !(sum1 > 0.f)) ? 0.f : 1.f / sum1;
+    __half* o0 = out16 + (static_cast<size_t>(smp) * S + r0) * 2 * d + h * 128 + 2 * t;
+    __half* o1 = out16 + (static_cast<size_t>(smp) * S + r1) * 2 * d + h * 128 + 2 * t;
+#pragma unroll
+    for (int nd = 0; nd < 16; ++nd) {
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      const __half* vrow = sVt + (nd * 8 + g) * VS + 2 * t;
+#pragma unroll
+      for (int kk = 0; kk < MAX_NT / 2; ++kk) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vrow + 16 * kk);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vrow + 16 * kk + 8);
+        mma_m16n8k16(o, phi[2 * kk][0], phi[2 * kk][1], phi[2 * kk + 1][0], phi[2 * kk + 1][1], b0, b1);
+        mma_m16n8k16(o, plo[2 * kk][0], plo[2 * kk][1], plo[2 * kk + 1][0], plo[2 * kk + 1][1], b0, b1);
+      }
+      if (r0 < S) *reinterpret_cast<__half2*>(o0 + nd * 8) = __floats2half2_rn(o[0] * inv0, o[1] * inv0);
+      if (r1 < S) *reinterpret_cast<__half2*>(o1 + nd * 8) = __floats2half2_rn(o[2] * inv1, o[3] * inv1);
+    }
   }
 }
 

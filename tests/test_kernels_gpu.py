@@ -55,6 +55,38 @@ def test_gemm_tcgen05(M, N, K, bn, act):
     assert err < 4e-3 * max(1.0, ref.abs().max().item()), err
 
 
+@pytest.mark.parametrize("n,S,Mt,ld_extra", [(5, 60, 16, 0), (3, 60, 16, 7168), (2, 17, 5, 0), (3, 100, 24, 0), (2, 64, 33, 1024),
+                                             (2, 61, 64, 0), (1, 1, 1, 0)])
+def test_cross_attention(n, S, Mt, ld_extra):
+    """The trans_dec cross-attention core (mma.sync tiles, P = hi + lo) against torch fp32: padding masks, token counts
+    that do not fill a key tile, rows that do not fill a 16-row tile, k | v embedded in a wider row (all-layer projection)."""
+    L, lib = _lib()
+    d, H, dh = 512, 4, 128
+    g = torch.Generator(device="cuda").manual_seed(100 * S + Mt)
+    q = torch.randn(n * S, d, device="cuda", generator=g).half()
+    ld = 2 * d + ld_extra
+    kvw = torch.randn(n * Mt, ld, device="cuda", generator=g).half()
+    col0 = ld_extra // 2 if ld_extra else 0                          # this "layer"'s k | v columns inside the wide row
+    col0 -= col0 % 8
+    mask = torch.rand(n, Mt, device="cuda", generator=g) < 0.3
+    mask[:, 0] = False                                               # the CLS token is never padding
+    out = torch.full((n * S, 2 * d), float("nan"), device="cuda", dtype=torch.float16)
+    kv_ptr = kvw.data_ptr() + 2 * col0
+    L.check(lib.b200mdm_test_cross_attention(_p(q), ctypes.c_void_p(kv_ptr), _p(mask.to(torch.uint8)), _p(out), n, S, Mt, ld,
+                                             _stream()))
+    torch.cuda.synchronize()
+    k = kvw[:, col0:col0 + d].float().view(n, Mt, H, dh).permute(0, 2, 1, 3)
+    v = kvw[:, col0 + d:col0 + 2 * d].float().view(n, Mt, H, dh).permute(0, 2, 1, 3)
+    qq = q.float().view(n, S, H, dh).permute(0, 2, 1, 3)
+    s = qq @ k.transpose(-1, -2) / dh ** 0.5
+    s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(n * S, d)
+    got = out[:, :d].float()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    assert err < 1.5e-3 * max(1.0, ref.abs().max().item()), err      # fp16 output rounding (2^-11 relative) dominates
+
+
 @pytest.mark.parametrize("impl", [0])
 @pytest.mark.parametrize("n,S,kv", [(3, 197, [197, 121, 58]), (2, 41, [41, 1]), (4, 61, [61, 46, 31, 2]), (1, 16, [16]),
                                     (2, 33, [20, 33]), (2, 256, [256, 130]), (2, 129, [129, 128])])
