@@ -20,6 +20,7 @@
 #include "epilogues.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
+#include "gemm2w.cuh"
 #include "gemm_ln.cuh"
 #include "postprocess.cuh"
 #include "qkv_attn.cuh"
@@ -253,6 +254,8 @@ static int init_kernel_attrs() {
   TRY((set_gemm2_attr<EpiBiasF16<true>>()));
   TRY((set_gemm2_attr<EpiBiasF16Wide<true>>()));
   TRY((set_gemm2_attr<EpiBiasF16Global>()));
+  CUDA_TRY(cudaFuncSetAttribute(gemm2w_f16_tcgen05<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2wSmem::TOTAL));
+  CUDA_TRY(cudaFuncSetAttribute(gemm2w_f16_tcgen05<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2wSmem::TOTAL));
   CUDA_TRY(cudaFuncSetAttribute(gemm_resid_ln_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmLnSmem::TOTAL));
   TRY((set_gemm_attr<128, EpiEmbed>()));
   TRY((set_gemm_attr<96, EpiOutStep>()));
@@ -322,6 +325,53 @@ static int launch_gemm2(const CUtensorMap& a, const CUtensorMap& b, const CUtens
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   CUDA_TRY(launch_k(gemm2_f16_tcgen05<Epi>, dim3(2 * clusters), dim3(GEMM2_THREADS), Gemm2Smem<Epi>::TOTAL, s, a, b, c, M, N, K, p));
   return B200MDM_OK;
+}
+
+// W-resident CTA-pair GEMM (gemm2w.cuh): K <= 512, every column block owned by at least one cluster.
+template <bool GELU>
+static int launch_gemm2w(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int M, int N, int K,
+                         const float* bias, cudaStream_t s, int num_sms) {
+  const int tiles_n = (N + GEMM2_BLOCK_N - 1) / GEMM2_BLOCK_N;
+  const int tiles = ((M + GEMM2_TILE_M - 1) / GEMM2_TILE_M) * tiles_n;
+  const int max_clusters = num_sms / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  if (K > GEMM2W_KB_MAX * GEMM_BLOCK_K || tiles_n > clusters)
+    return fail(B200MDM_ENOTIMPL, "W-resident pair GEMM needs K <= %d and N <= %d", GEMM2W_KB_MAX * GEMM_BLOCK_K, clusters * GEMM2_BLOCK_N);
+  typename EpiBiasF16<GELU>::Params p{bias};
+  CUDA_TRY(launch_k(gemm2w_f16_tcgen05<GELU>, dim3(2 * clusters), dim3(GEMM2_THREADS), Gemm2wSmem::TOTAL, s, a, b, c, M, N, K, p));
+  return B200MDM_OK;
+}
+// The W-resident order binds a cluster to one column block: it pays when that costs no extra round of tiles compared
+// with the strided order of the streaming kernel (rounds = tiles on the busiest cluster).  B200MDM_GEMM2W=0 in the
+// environment keeps the streaming kernel everywhere (A/B timing).
+static bool gemm2w_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200MDM_GEMM2W");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+static bool gemm2w_pays(int M, int N, int K, int num_sms) {
+  if (!gemm2w_enabled() || K > GEMM2W_KB_MAX * GEMM_BLOCK_K) return false;
+  const int tiles_m = (M + GEMM2_TILE_M - 1) / GEMM2_TILE_M;
+  const int tiles_n = (N + GEMM2_BLOCK_N - 1) / GEMM2_BLOCK_N;
+  const int tiles = tiles_m * tiles_n;
+  const int max_clusters = num_sms / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  if (tiles_n > clusters) return false;
+  const int rounds_strided = (tiles + clusters - 1) / clusters;
+  const int owners = clusters / tiles_n;   // clusters of the least-served column block
+  const int rounds_resident = (tiles_m + owners - 1) / owners;
+  return rounds_resident <= rounds_strided;
+}
+// out16 = fp16(act(A W^T + bias)) on CTA pairs: W-resident kernel where it pays, streaming kernel otherwise
+template <bool GELU>
+static int launch_gemm2_bias(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, int M, int N, int K,
+                             const float* bias, cudaStream_t s, int num_sms) {
+  if (gemm2w_pays(M, N, K, num_sms)) return launch_gemm2w<GELU>(a, b, c, M, N, K, bias, s, num_sms);
+  typename EpiBiasF16<GELU>::Params p{bias};
+  return launch_gemm2<EpiBiasF16<GELU>>(a, b, c, M, N, K, p, s, num_sms);
 }
 
 // h <- LayerNorm(h + A W^T + bias), 2-CTA cluster splitting the 512 columns, LayerNorm statistics exchanged through
@@ -1025,8 +1075,7 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
         // trans_dec keeps [hi | lo] activations only where the precision study needs them (self-attention output,
         // FFN-up input, FFN-down input: oracle emulation 6.2e-4 vs 5.1e-4 with every site split, tolerance 1e-3); the
         // projections below read the hi half alone: K = d against the first d columns of [W | W]
-        EpiBiasF16<false>::Params p{w.bqkv};
-        TRY((launch_gemm2<EpiBiasF16<false>>(e->m_h16, w.m_wqkv, e->m_qkv_st, e->M, 3 * d, d, p, s, e->num_sms)));
+        TRY((launch_gemm2_bias<false>(e->m_h16, w.m_wqkv, e->m_qkv_st, e->M, 3 * d, d, w.bqkv, s, e->num_sms)));
       }
       AttnMaps am{e->m_att_q, e->m_att_kv, e->m_att_o};
       TRY(launch_attention_tc(am, e->kvlen, e->Bp, S, d, e->H, s, wide));
@@ -1034,10 +1083,7 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
     if (!B200_SKIP(2)) TRY(launch_gemm_resid_ln(e->m_att, w.m_wo_256, e->m_res, e->M, kw * d, w.bo, w.g1, w.be1, s, e->num_sms));
     if (e->dec) {
       // cross-attention block of nn.TransformerDecoderLayer: q from the sequence, k/v from the text memory
-      {
-        EpiBiasF16<false>::Params p{w.bq_c};
-        TRY((launch_gemm2<EpiBiasF16<false>>(e->m_h16, w.m_wq_c, e->m_qc_st, e->M, d, d, p, s, e->num_sms)));
-      }
+      TRY((launch_gemm2_bias<false>(e->m_h16, w.m_wq_c, e->m_qc_st, e->M, d, d, w.bq_c, s, e->num_sms)));
       {
         const float sl2 = 1.4426950408889634f / sqrtf(128.0f);
         const dim3 cg(e->H, e->Bp), cb(128);
@@ -1057,8 +1103,8 @@ static int enqueue_forward(b200mdm_engine* e, const StepArgs& a, cudaStream_t s,
       EpiBiasF16Wide<true>::Params p{w.b1, ff};
       TRY((launch_gemm2<EpiBiasF16Wide<true>>(e->m_h16, w.m_w1, e->m_ffn_st, e->M, ff, kw * d, p, s, e->num_sms)));
     } else if (!B200_SKIP(4)) {
-      EpiBiasF16<true>::Params p{w.b1};
-      TRY((launch_gemm2<EpiBiasF16<true>>(e->m_h16, w.m_w1, e->m_ffn_st, e->M, ff, d, p, s, e->num_sms)));
+      // K = d: each CTA's half of a W1 tile stays in shared memory for the whole launch (gemm2w.cuh)
+      TRY((launch_gemm2_bias<true>(e->m_h16, w.m_w1, e->m_ffn_st, e->M, ff, d, w.b1, s, e->num_sms)));
     }
     if (!B200_SKIP(8)) TRY(launch_gemm_resid_ln(e->m_ffn, w.m_w2_256, e->m_res, e->M, kw * ff, w.b2, e->dec ? w.g3 : w.g2,
                              e->dec ? w.be3 : w.be2, s, e->num_sms));
@@ -1300,11 +1346,13 @@ extern "C" int b200mdm_test_gemm_f16(const void* a16_dev, const void* w16_dev, c
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (block_n == 512) {  // CTA-pair kernel, 256 x 256 pair tiles
+  if (block_n == 512 || block_n == 513) {  // CTA-pair kernels, 256 x 256 pair tiles: 512 streaming, 513 W-resident
     CUtensorMap ma, mb, mc;
     TRY(make_map(&ma, a16_dev, M, K, K, GEMM_BLOCK_M));
     TRY(make_map(&mb, w16_dev, N, K, K, 128));
     TRY(make_map_t(&mc, out16_dev, 2, M, N, N, 32));
+    if (block_n == 513)
+      return act ? launch_gemm2w<true>(ma, mb, mc, M, N, K, bias_dev, s, sms) : launch_gemm2w<false>(ma, mb, mc, M, N, K, bias_dev, s, sms);
     if (act) {
       EpiBiasF16<true>::Params p{bias_dev};
       return launch_gemm2<EpiBiasF16<true>>(ma, mb, mc, M, N, K, p, s, sms);
@@ -1313,7 +1361,7 @@ extern "C" int b200mdm_test_gemm_f16(const void* a16_dev, const void* w16_dev, c
     return launch_gemm2<EpiBiasF16<false>>(ma, mb, mc, M, N, K, p, s, sms);
   }
   if (block_n == 128) return test_gemm_bn<128>(a16_dev, w16_dev, bias_dev, out16_dev, M, N, K, act, s, sms);
-  return fail(B200MDM_EINVAL, "block_n must be 512 (CTA pair) or 128 (single CTA)");
+  return fail(B200MDM_EINVAL, "block_n must be 512 (CTA pair), 513 (CTA pair, W-resident) or 128 (single CTA)");
 }
 
 extern "C" int b200mdm_test_attention(const void* qkv16_dev, void* out16_dev, const int32_t* kvlen_dev,

@@ -37,6 +37,14 @@ def _stream():
     (3000, 1024, 512, 512, 1),       # pair: FFN up + GELU
     (130, 512, 1024, 512, 0),        # pair: second CTA holds 2 live rows only
     (100, 264, 512, 512, 0),         # pair: second CTA entirely out of range, N tail
+    (256, 256, 64, 513, 0),          # W-resident pair kernel (gemm2w.cuh): one tile, one resident k-block
+    (700, 512, 512, 513, 0),         # W-resident: M tail inside the second CTA, one tile per cluster
+    (25216 // 8, 1536, 512, 513, 0), # W-resident: QKV shape, 6 column blocks
+    (25216, 1024, 512, 513, 1),      # W-resident: the FFN up-projection at BASELINE config 2 (6 rounds per cluster: A ring
+                                     # and both accumulator stages wrap while W stays put) + GELU
+    (40000, 512, 320, 513, 0),       # W-resident: 5 k-blocks against a 4-slot A ring, 5 rounds
+    (5000, 768, 200, 513, 1),        # W-resident: K tail inside the last k-block (200 = 3*64 + 8)
+    (100, 264, 512, 513, 0),         # W-resident: second CTA entirely out of range, N tail
 ])
 def test_gemm_tcgen05(M, N, K, bn, act):
     L, lib = _lib()
