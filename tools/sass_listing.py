@@ -1,6 +1,6 @@
 """Per-kernel SASS evidence for profiles/: counts of the Blackwell-native mnemonics (UTC*MMA = tcgen05.mma, LDTM/STTM =
-tcgen05.ld/st, UTMALDG/UTMASTG = TMA, UBLKCP = bulk copy, SYNCS = mbarrier, USETMAXREG = setmaxnreg) and of the legacy
-tensor path (HMMA) in every kernel of libb200mdm.so.   python tools/sass_listing.py > profiles/r02_sass_kernels.txt"""
+tcgen05.ld/st, UTMALDG/UTMASTG = TMA, UBLKCP = bulk copy, SYNCS = mbarrier, USETMAXREG = setmaxnreg) of the packed fp32
+instructions (FFMA2 / FADD2 / FMUL2 = fma/add/mul.f32x2) and of the legacy tensor path (HMMA) in every kernel of libb200mdm.so.   python tools/sass_listing.py > profiles/r02_sass_kernels.txt"""
 import collections
 import os
 import re
@@ -9,7 +9,7 @@ import sys
 
 LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "motion-diffusion-model_b200", "lib", "libb200mdm.so")
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
-MN = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "SYNCS", "USETMAXREG", "HMMA", "MUFU", "STS", "LDS", "STG", "LDG"]
+MN = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "SYNCS", "USETMAXREG", "HMMA", "FFMA2", "FADD2", "FMUL2", "MUFU", "STS", "LDS", "STG", "LDG"]
 cur, per = None, collections.OrderedDict()
 for line in sass.splitlines():
     m = re.search(r"Function : (\S+)", line)
