@@ -56,83 +56,107 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md clocks line).
+
+    Two independent sources, both opened BEFORE the warm-up so that their start-up cost (nvmlInit, the first nvidia-smi
+    line) is not paid inside the region: an in-process NVML poll every 20 ms (a 0.4 s region still gets ~20 samples) and
+    an `nvidia-smi -lms 100` child whose lines are time-stamped on arrival.  stop() reports the NVML samples taken between
+    start() and stop(); if there are none (r02_p: one run in five came back empty, every poll raising), the nvidia-smi
+    lines of the same window; if there are none either, one synchronous sample taken at stop() -- the GPU has just
+    finished the last step -- and says so in `source`."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = (0x8, 0x40, 0x20, 0x4)   # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
-        self.nvml, self.handle, self.stop_flag, self.thread = None, None, False, None
-
-    # NVML in-process (20 ms period: a 0.4 s timed region still gets ~20 samples); nvidia-smi -lms as the fallback
-    def _nvml_open(self):
+    def __init__(self, gpu_index, enabled=True):
+        self.idx, self.proc, self.nvml, self.handle = gpu_index, None, None, None
+        self.nvml_rows, self.smi_rows, self.errors = [], [], []
+        self.t0, self.t1, self.stop_flag, self.thread = None, None, False, None
+        if not enabled:
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
-            h = None
             try:
                 import torch
-                uuid = str(torch.cuda.get_device_properties(self.idx).uuid)
-                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)).encode())
             except Exception:
-                h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
             self.nvml, self.handle = pynvml, h
-            return True
-        except Exception:
-            return False
+            self._nvml_sample()           # pays the first-call cost outside the region; raises if NVML is unusable
+        except Exception as e:            # noqa: BLE001
+            self.errors.append("nvml open: %r" % (e,))
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+            import atexit
+            atexit.register(lambda p=self.proc: p.poll() is None and p.terminate())   # never leave the child behind
+        except Exception as e:            # noqa: BLE001
+            self.errors.append("nvidia-smi: %r" % (e,))
+            self.proc = None
+
+    def _nvml_sample(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = int(get(self.handle))
+        return (time.perf_counter(), int(sm), int(mx), [nm for b, nm in zip(self.BITS, self.NAMES) if bits & b])
 
     def _nvml_poll(self):
-        n = self.nvml
-        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
         while not self.stop_flag:
             try:
-                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
-                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
-                get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
-                bits = int(get(self.handle))
-                row = ["", str(sm), str(mx), "", ""] + ["Active" if bits & b else "Not Active" for b in (0x8, 0x40, 0x20, 0x4)]
-                self.rows.append(row)
-            except Exception:
-                pass
+                self.nvml_rows.append(self._nvml_sample())
+            except Exception as e:        # noqa: BLE001
+                if len(self.errors) < 4:
+                    self.errors.append("nvml poll: %r" % (e,))
             time.sleep(0.02)
-        del names
-
-    def start(self):
-        if self._nvml_open():
-            self.thread = threading.Thread(target=self._nvml_poll, daemon=True)
-            self.thread.start()
-            return
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            c = [x.strip() for x in line.split(",")]
+            if len(c) >= 9 and c[1].isdigit() and c[2].isdigit():
+                self.smi_rows.append((time.perf_counter(), int(c[1]), int(c[2]),
+                                      [nm for nm, v in zip(self.NAMES, c[5:9]) if v.lower().startswith("active")]))
+
+    def start(self):
+        self.t0 = time.perf_counter()
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._nvml_poll, daemon=True)
+            self.thread.start()
 
     def stop(self):
+        self.t1 = time.perf_counter()
+        if self.t0 is None:
+            self.t0 = self.t1
+        self.stop_flag = True
         if self.thread is not None:
-            self.stop_flag = True
             self.thread.join(timeout=1.0)
-        elif self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        else:
-            time.sleep(0.25)
+        if self.proc is not None:
+            time.sleep(0.12)              # the line that covers the end of the region
             self.proc.terminate()
-        sm = sorted(int(r[1]) for r in self.rows if len(r) > 2 and r[1].isdigit())
-        mx = [int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows),
-                "source": "nvml 20 ms" if self.thread is not None else "nvidia-smi -lms 200"}
+        window = lambda rows: [r for r in rows if self.t0 <= r[0] <= self.t1 + 0.12]
+        rows, source = window(self.nvml_rows), "nvml 20 ms"
+        if not rows:
+            rows, source = window(self.smi_rows), "nvidia-smi -lms 100"
+        if not rows and self.nvml is not None:
+            try:
+                rows, source = [self._nvml_sample()], "nvml, ONE sample at the end of the timed region (no in-region sample)"
+            except Exception as e:        # noqa: BLE001
+                self.errors.append("nvml final: %r" % (e,))
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0,
+                    "source": "none", "errors": self.errors}
+        sm = sorted(r[1] for r in rows)
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[2] for r in rows),
+               "reasons": sorted({nm for r in rows for nm in r[3]}), "samples": len(rows), "source": source}
+        if self.errors:
+            out["errors"] = self.errors
+        return out
 
 
 def make_args(**over):
@@ -451,7 +475,7 @@ def kernel_roofline(dev, peaks, B):
         Wt = (torch.randn(N, K, device=dev) / K ** 0.5).half()
         bias = torch.zeros(N, device=dev)
         O = torch.empty(M, N, device=dev, dtype=torch.float16)
-        ms = time_kernel(lambda: _lib.check(lib.b200mdm_test_gemm_f16(A.data_ptr(), Wt.data_ptr(), bias.data_ptr(), O.data_ptr(), M, N, K, act, 512, st)))
+        ms = time_kernel(lambda: _lib.check(lib.b200mdm_test_gemm_f16(A.data_ptr(), Wt.data_ptr(), bias.data_ptr(), O.data_ptr(), M, N, K, act, 513 if K <= 512 else 512, st)))   # 513: the W-resident pair GEMM the step dispatches at K <= 512
         return 2.0 * M * N * K, ms
 
     def ln_case(K):
@@ -477,7 +501,7 @@ def kernel_roofline(dev, peaks, B):
     cases = [("qkv_attention_kernel (fused QKV projection + softmax attention, 128 sequences x 4 heads, S=197)", qkv_attn_case),
              ("gemm_resid_ln_cluster FFN-down + residual + LayerNorm M=%d N=512 K=1024" % M, lambda: ln_case(FF)),
              ("gemm_resid_ln_cluster out-proj + residual + LayerNorm K=512", lambda: ln_case(D)),
-             ("gemm2_f16_tcgen05<bias,gelu> FFN-up N=1024 K=512", lambda: gemm_case(FF, D, 1))]
+             ("gemm2w_f16_tcgen05<gelu> (W-resident pair GEMM) FFN-up N=1024 K=512", lambda: gemm_case(FF, D, 1))]
     rows = []
     for name, fn in cases:
         fl, ms = fn()
@@ -536,16 +560,27 @@ def main():
             print("[bench %.1fs] %s" % (time.perf_counter() - t_start, msg), file=sys.stderr, flush=True)
 
     t_start = time.perf_counter()
+    try:
+        sampler = ClockSampler(local, enabled=(rank == 0))   # NVML / nvidia-smi opened before the warm-up, sampled in the region
+    except Exception as e:   # noqa: BLE001  (a broken sampler must not take the measurement down with it)
+        sampler = ClockSampler(local, enabled=False)
+        sampler.errors.append("sampler: %r" % (e,))
     for _ in range(max(a.warmup, 3)):
         one_loop_resident()
     torch.cuda.synchronize()
     log("warm-up done")
     eng.launch_count(reset=True)
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        try:
+            sampler.start()
+        except Exception as e:   # noqa: BLE001
+            sampler.errors.append("start: %r" % (e,))
     ms_total = timed(one_loop_resident, a.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    try:
+        clocks = sampler.stop() if rank == 0 else None
+    except Exception as e:   # noqa: BLE001
+        clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling failed"], "samples": 0, "source": "none",
+                  "errors": ["stop: %r" % (e,)]}
     launches = eng.launch_count(reset=True)
     log("resident loops timed: %.2f ms per loop" % (ms_total / a.steps))
     for _ in range(2):

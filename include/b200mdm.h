@@ -186,8 +186,9 @@ int b200mdm_recover_from_ric(const float* data_dev, int64_t stride_b, int64_t st
 
 /* ---- kernel-level entry points (used by tests/ to check each kernel against a torch fp32 restatement) ---- */
 /* out16[M,N] = fp16(act(A16[M,K] @ W16[N,K]^T + bias)); act: 0 none, 1 exact GELU.  K % 8 == 0, N % 8 == 0,
- * block_n: 512 = CTA-pair kernel (256 x 256 tiles, the one the layer GEMMs use), 128 = single-CTA kernel (the mainloop
- * the embedding / output projections use). */
+ * block_n: 512 = CTA-pair kernel (256 x 256 tiles, operands streamed), 513 = CTA-pair kernel with its half of a W tile
+ * resident in shared memory (K <= 512 and N <= 256 x the number of clusters, B200MDM_ENOTIMPL otherwise; the kernel the
+ * step dispatches for the FFN up-projection), 128 = single-CTA kernel (the mainloop the embedding / output projections use). */
 int b200mdm_test_gemm_f16(const void* a16_dev, const void* w16_dev, const float* bias_dev, void* out16_dev, int32_t M,
                           int32_t N, int32_t K, int32_t act, int32_t block_n, void* stream);
 /* out16[n*S, d] = softmax(q k^T / sqrt(128) + mask) v per (sample, head); qkv16 [n*S, 3d]; kvlen int32 [n] device.
