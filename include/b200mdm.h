@@ -213,6 +213,14 @@ int b200mdm_test_qkv_attention(const void* h16_dev, int32_t ld, const void* wqkv
 int b200mdm_test_gemm_resid_ln(const void* a16_dev, const void* w16_dev, const float* bias_dev, const float* gamma_dev,
                                const float* beta_dev, void* hres16_dev, int32_t M, int32_t K, void* stream);
 
+/* Host-only (no CUDA call): which CTA-pair GEMM the step would dispatch for out16[M,N] = act(A[M,K] W[N,K]^T + bias) on a
+ * device with num_sms SMs, and the tile order it implies.  plan_out[0] = 1 if the W-resident kernel is chosen (0: streaming),
+ * plan_out[1] = clusters launched, plan_out[2] = rounds of tiles on the busiest cluster with the strided order of the
+ * streaming kernel, plan_out[3] = the same with the W-resident order (-1 if that kernel cannot run the shape).  If
+ * tile_owner is not NULL it receives, for the W-resident order, the cluster that owns tile (m_blk, n_blk) at
+ * tile_owner[m_blk * tiles_n + n_blk] (tiles_m = ceil(M / 256), tiles_n = ceil(N / 256)), -1 for a tile nobody owns. */
+int b200mdm_test_gemm2_plan(int32_t M, int32_t N, int32_t K, int32_t num_sms, int32_t* plan_out, int32_t* tile_owner);
+
 #ifdef __cplusplus
 }
 #endif

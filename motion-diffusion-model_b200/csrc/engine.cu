@@ -1364,6 +1364,37 @@ extern "C" int b200mdm_test_gemm_f16(const void* a16_dev, const void* w16_dev, c
   return fail(B200MDM_EINVAL, "block_n must be 512 (CTA pair), 513 (CTA pair, W-resident) or 128 (single CTA)");
 }
 
+// Host-only: the dispatch decision of launch_gemm2_bias and the tile ownership of the W-resident order (the same
+// arithmetic gemm2w_f16_tcgen05 does on the device), for the CPU tests.
+extern "C" int b200mdm_test_gemm2_plan(int32_t M, int32_t N, int32_t K, int32_t num_sms, int32_t* plan_out, int32_t* tile_owner) {
+  if (M <= 0 || N <= 0 || K <= 0 || num_sms < 2 || !plan_out) return fail(B200MDM_EINVAL, "bad argument");
+  const int tiles_m = (M + GEMM2_TILE_M - 1) / GEMM2_TILE_M, tiles_n = (N + GEMM2_BLOCK_N - 1) / GEMM2_BLOCK_N;
+  const int tiles = tiles_m * tiles_n, max_clusters = num_sms / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  const bool can = K <= GEMM2W_KB_MAX * GEMM_BLOCK_K && tiles_n <= clusters;
+  plan_out[0] = gemm2w_pays(M, N, K, num_sms) ? 1 : 0;
+  plan_out[1] = clusters;
+  plan_out[2] = (tiles + clusters - 1) / clusters;
+  plan_out[3] = -1;
+  if (tile_owner)
+    for (int i = 0; i < tiles; ++i) tile_owner[i] = -1;
+  if (can) {
+    int rounds = 0;
+    for (int c = 0; c < clusters; ++c) {
+      const int n_blk = c % tiles_n, m_first = c / tiles_n, m_step = (clusters - n_blk + tiles_n - 1) / tiles_n;
+      int mine = 0;
+      for (int m_blk = m_first; m_blk < tiles_m; m_blk += m_step, ++mine)
+        if (tile_owner) {
+          int32_t& o = tile_owner[m_blk * tiles_n + n_blk];
+          o = (o == -1) ? c : -2;   // -2: two owners (never happens; the test checks)
+        }
+      rounds = mine > rounds ? mine : rounds;
+    }
+    plan_out[3] = rounds;
+  }
+  return B200MDM_OK;
+}
+
 extern "C" int b200mdm_test_attention(const void* qkv16_dev, void* out16_dev, const int32_t* kvlen_dev,
                                       int32_t n_samples, int32_t S, int32_t d, int32_t impl, void* stream) {
   if (!qkv16_dev || !out16_dev || !kvlen_dev || n_samples <= 0 || S <= 0) return fail(B200MDM_EINVAL, "bad argument");

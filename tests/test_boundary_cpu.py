@@ -163,3 +163,33 @@ def test_engine_for_rejects_foreign_wrappers():
     model, _ = b200mdm.create_model_and_diffusion(default_args(layers=1), SimpleNamespace(dataset=SimpleNamespace()))
     with pytest.raises(TypeError):
         engine_for(SimpleNamespace(model=model))
+
+
+@pytest.mark.parametrize("M,N,K,sms", [(25216, 1024, 512, 148), (7808, 1536, 512, 148), (15360, 1536, 512, 148), (15360, 512, 512, 148),
+                                       (256, 256, 64, 148), (100, 264, 512, 148), (50000, 8192, 512, 148), (25216, 1024, 1024, 148),
+                                       (300, 18944, 512, 148), (300, 19200, 512, 148), (25216, 1024, 512, 132), (999, 512, 200, 8)])
+def test_pair_gemm_dispatch_plan(M, N, K, sms):
+    """Host logic of the CTA-pair GEMM dispatch (csrc/gemm2w.cuh): with the W-resident tile order every tile has exactly
+    one owner, a cluster only ever touches one column block, and the kernel is chosen only where it costs no extra round
+    of tiles against the strided order of the streaming kernel (and never for K > 512 or more column blocks than clusters)."""
+    from b200mdm import _lib
+    lib = _lib.load()
+    tm, tn = -(-M // 256), -(-N // 256)
+    plan = (ctypes.c_int32 * 4)()
+    owner = (ctypes.c_int32 * (tm * tn))()
+    _lib.check(lib.b200mdm_test_gemm2_plan(M, N, K, sms, plan, owner))
+    chosen, clusters, rounds_strided, rounds_resident = list(plan)
+    assert clusters == min(tm * tn, sms // 2) and rounds_strided == -(-tm * tn // clusters)
+    can = K <= 512 and tn <= clusters
+    if not can:
+        assert chosen == 0 and rounds_resident == -1
+        return
+    own = list(owner)
+    assert all(0 <= o < clusters for o in own), "a tile without owner / with two owners"
+    per_cluster = {}
+    for i, o in enumerate(own):
+        per_cluster.setdefault(o, []).append(i % tn)
+    assert all(len(set(cols)) == 1 for cols in per_cluster.values()), "a cluster spans two column blocks: W would not stay resident"
+    assert max(len(v) for v in per_cluster.values()) == rounds_resident
+    if os.environ.get("B200MDM_GEMM2W", "1") != "0":
+        assert chosen == int(rounds_resident <= rounds_strided)
